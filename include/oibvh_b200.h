@@ -1,0 +1,169 @@
+/*
+ * oibvh_b200 -- C ABI of the B200-native oibvh collision path (build, refit, broad phase, narrow phase).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, opaque handles, int status codes. The reference
+ * (hhhcbw/oibvh) has no FFI layer -- its host classes launch kernels inline -- so each entry point below names
+ * the reference host method it replaces (paths relative to the reference checkout). The C++ facade in
+ * include/oibvh/*.hpp re-creates the reference's classes (Mesh, OibvhTree, Scene, DeviceType, aabb_box_t,
+ * int_tri_pair_node_t) on top of exactly these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns OIBVH_OK (0) or a negative oibvh_status; oibvh_last_error() gives the text of the
+ *     last failure on the calling thread. No exceptions cross the boundary.
+ *   - a context binds one CUDA device and one stream. Handles are not thread-safe; distinct contexts may be
+ *     used from distinct threads.
+ *   - "host" pointers are caller-owned host memory (pageable or pinned); "dev" pointers are device memory on the
+ *     context's device. Nothing is retained after the call returns unless stated.
+ *   - build/refit/transform/detect_async only ENQUEUE work on the context stream. Calls that return data to
+ *     the host (download*, detect, get_counts, get_pairs) synchronise the stream first.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with OIBVH_ERR_CUDA.
+ *
+ * Record layouts (bit-compatible with the reference, include/utils/utils.h:13-61):
+ *   oibvh_aabb          24 B  { float min[3]; float max[3]; }                     == aabb_box_t
+ *   oibvh_int_tri_pair  16 B  { uint32 bvh_index[2]; uint32 tri_index[2]; }       == int_tri_pair_node_t
+ * tri_index values are positions in the tree's Morton-sorted face array, exactly like the reference GPU path
+ * (src/cuda/collide.cu:296-297); oibvh_tree_download(perm) maps them back to input face ids.
+ */
+#ifndef OIBVH_B200_H
+#define OIBVH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oibvh_ctx oibvh_ctx;
+typedef struct oibvh_tree oibvh_tree;
+typedef struct oibvh_scene oibvh_scene;
+typedef struct oibvh_graph oibvh_graph;
+
+typedef struct oibvh_aabb
+{
+    float min[3];
+    float max[3];
+} oibvh_aabb;
+
+typedef struct oibvh_int_tri_pair
+{
+    uint32_t bvh_index[2];
+    uint32_t tri_index[2];
+} oibvh_int_tri_pair;
+
+typedef enum oibvh_status
+{
+    OIBVH_OK = 0,
+    OIBVH_ERR_INVALID = -1,  /* bad argument / wrong state (e.g. scene_add_tree before build) */
+    OIBVH_ERR_CUDA = -2,     /* a CUDA runtime call or kernel failed (includes "no device") */
+    OIBVH_ERR_NOMEM = -3,    /* device or host allocation failed */
+    OIBVH_ERR_OVERFLOW = -4, /* a work queue could not be grown enough to hold the BVTT front / pair list */
+    OIBVH_ERR_INTERNAL = -5
+} oibvh_status;
+
+/* stage ids for oibvh_ctx_stage_ms */
+enum
+{
+    OIBVH_STAGE_BUILD = 0,
+    OIBVH_STAGE_REFIT = 1,
+    OIBVH_STAGE_BROAD = 2,
+    OIBVH_STAGE_NARROW = 3,
+    OIBVH_STAGE_COUNT = 4
+};
+
+const char* oibvh_last_error(void);
+/* library/ABI version: major*10000 + minor*100 + patch */
+int oibvh_version(void);
+/* number of CUDA devices visible (0 without a GPU); never fails */
+int oibvh_device_count(void);
+
+/* ---- context: replaces the implicit "current device, default stream" of the reference
+ *      (Scene::detectCollisionOnGPU cudaSetDevice, src/cuda/scene.cu:229) --------------------------------- */
+int oibvh_ctx_create(int device, oibvh_ctx** out);
+/* same, but enqueue on a caller-owned cudaStream_t (e.g. the framework's current stream); 0 = legacy default */
+int oibvh_ctx_create_on_stream(int device, void* cuda_stream, oibvh_ctx** out);
+int oibvh_ctx_destroy(oibvh_ctx* ctx);
+int oibvh_ctx_synchronize(oibvh_ctx* ctx);
+int oibvh_ctx_get_stream(oibvh_ctx* ctx, void** cuda_stream);
+/* number of kernel launches this context has enqueued so far (graph replays count their kernel nodes) */
+int oibvh_ctx_launch_count(oibvh_ctx* ctx, uint64_t* launches);
+/* enable per-stage CUDA-event timing (adds event records, no host syncs); read the last values with stage_ms.
+ * Replaces the reference's kernelLaunch() stopwatch (include/cuda/utils.cuh:36-59), without its per-launch sync. */
+int oibvh_ctx_enable_timing(oibvh_ctx* ctx, int enable);
+int oibvh_ctx_stage_ms(oibvh_ctx* ctx, float ms[OIBVH_STAGE_COUNT]);
+
+/* ---- whole-frame CUDA graphs: everything enqueued on this context between begin and end (transform, build, refit,
+ *      detect_async) is recorded instead of executed and can then be replayed with one launch. The reference has
+ *      no counterpart (it synchronises after every kernel). Handles used inside must have run once before (buffers
+ *      allocated); a graph becomes stale -- launch returns OIBVH_ERR_INVALID -- if a work queue is regrown later. */
+int oibvh_ctx_capture_begin(oibvh_ctx* ctx);
+int oibvh_ctx_capture_end(oibvh_ctx* ctx, oibvh_graph** out);
+int oibvh_graph_launch(oibvh_graph* graph);
+int oibvh_graph_destroy(oibvh_graph* graph);
+
+/* ---- tree: OibvhTree (include/cuda/oibvhTree.cuh:44-93) ------------------------------------------------- */
+/* OibvhTree(mesh) + setup() (src/cuda/oibvhTree.cu:9-15, 157-174): takes packed xyz positions [V*3], triangle
+ * indices [T*3] and the mesh AABB computed at Mesh construction (src/utils/mesh.cpp:91-98; min xyz, max xyz),
+ * uploads them once. T >= 2 (the reference underflows for T = 1, oibvhTree.cu:317-322). */
+int oibvh_tree_create(oibvh_ctx* ctx, const float* host_positions, uint32_t V, const uint32_t* host_indices,
+                      uint32_t T, const float mesh_aabb[6], oibvh_tree** out);
+/* same with inputs already resident in device memory (copied device-to-device, the caller keeps its buffers) */
+int oibvh_tree_create_from_device(oibvh_ctx* ctx, const float* dev_positions, uint32_t V,
+                                  const uint32_t* dev_indices, uint32_t T, const float mesh_aabb[6],
+                                  oibvh_tree** out);
+/* OibvhTree(other, mesh) copy constructor (src/cuda/oibvhTree.cu:17-33): same sorted faces / permutation /
+ * node array / positions as `other`, sharing nothing on the device. */
+int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out);
+int oibvh_tree_destroy(oibvh_tree* tree);
+/* the "copy Mesh positions" head of OibvhTree::refit (src/cuda/oibvhTree.cu:196-199, 208) */
+int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_positions);
+int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const float* dev_positions);
+/* Mesh::transform / transform_vec4_kernel (src/utils/mesh.cpp:187-213, src/cuda/transform.cu:18-40) applied to the
+ * device-resident positions: p = M * (p, 1), column-major M, glm operation order, no FMA contraction. */
+int oibvh_tree_transform(oibvh_tree* tree, const float M[16]);
+/* OibvhTree::build (src/cuda/oibvhTree.cu:237-388): Morton keys, stable sort, implicit-layout AABB reduction */
+int oibvh_tree_build(oibvh_tree* tree);
+/* OibvhTree::refit (src/cuda/oibvhTree.cu:193-235) on the positions currently on the device */
+int oibvh_tree_refit(oibvh_tree* tree);
+/* getPrimCount / vertex count / oibvh_get_size(T) / getDepth() = ilog2(N)  (oibvhTree.cu:45-53) */
+int oibvh_tree_get_info(const oibvh_tree* tree, uint32_t* T, uint32_t* V, uint32_t* N, uint32_t* depth);
+int oibvh_tree_is_built(const oibvh_tree* tree, int* built);
+/* results the reference copies back after every build/refit (oibvhTree.cu:232, 375-377): nodes [N] in real-index
+ * order, sorted faces [T*3]; plus perm [T] (sorted position -> input face id), which the reference discards.
+ * Any pointer may be NULL. Synchronises. */
+int oibvh_tree_download(oibvh_tree* tree, oibvh_aabb* host_nodes, uint32_t* host_sorted_faces, uint32_t* host_perm);
+int oibvh_tree_download_positions(oibvh_tree* tree, float* host_positions);
+/* sorted 30-bit Morton keys [T] of the last build (debug / parity) */
+int oibvh_tree_download_keys(oibvh_tree* tree, uint32_t* host_sorted_keys);
+/* device views for zero-copy consumers (valid until the tree is destroyed) */
+int oibvh_tree_device_views(oibvh_tree* tree, const oibvh_aabb** dev_nodes, const uint32_t** dev_sorted_faces,
+                            const float** dev_positions);
+
+/* ---- scene: Scene (include/cuda/scene.cuh:26-67) -------------------------------------------------------- */
+int oibvh_scene_create(oibvh_ctx* ctx, oibvh_scene** out);
+int oibvh_scene_destroy(oibvh_scene* scene);
+/* Scene::addOibvhTree (src/cuda/scene.cu:95-129); the tree must be built; bvh index = insertion order.
+ * Trees are referenced, not copied: refits between detections are honoured like in the reference. */
+int oibvh_scene_add_tree(oibvh_scene* scene, oibvh_tree* tree);
+/* restrict this scene to shard `rank` of `world` (seed BVTT nodes are dealt round-robin); default 0 of 1 */
+int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world);
+/* Scene::detectCollision(GPUx, entryLevel, expandLevels) (src/cuda/scene.cu:157-185, 225-446): broad + narrow phase
+ * over all object pairs i<j. entry_level / expand_levels keep the reference meaning (seed level; levels descended
+ * per round, 0 = choose adaptively); the resulting pair SET does not depend on them.
+ * n_candidates may be NULL. Synchronises. */
+int oibvh_scene_detect(oibvh_scene* scene, uint32_t entry_level, uint32_t expand_levels, uint32_t* n_pairs,
+                       uint32_t* n_candidates);
+/* enqueue only; read the result with oibvh_scene_get_counts */
+int oibvh_scene_detect_async(oibvh_scene* scene, uint32_t entry_level, uint32_t expand_levels);
+int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_candidates);
+/* Scene::m_intTriPairs (scene.cu:414-416): n_pairs records, order unspecified (as in the reference) */
+int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs);
+/* device view of the pair list of the last detection (for a collective gather by the caller) */
+int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs);
+/* per-round BVTT statistics of the last detection: tested[r] nodes were overlap-tested in round r.
+ * Returns the number of rounds written (<= max_rounds). */
+int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds, uint32_t* n_rounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OIBVH_B200_H */

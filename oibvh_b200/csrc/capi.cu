@@ -1,0 +1,937 @@
+// C ABI of oibvh_b200 (see include/oibvh_b200.h): handle management, device memory, kernel schedules.
+// No CPU fallback lives here: every compute entry point enqueues CUDA kernels or fails.
+#include "../../include/oibvh_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace oibvh;
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                                 \
+    do                                                                                                           \
+    {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return fail(e__ == cudaErrorMemoryAllocation ? OIBVH_ERR_NOMEM : OIBVH_ERR_CUDA, "%s:%d %s -> %s",   \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e__));                                     \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                                       \
+    do                                                                                                           \
+    {                                                                                                            \
+        if (!(cond)) return fail(OIBVH_ERR_INVALID, "%s: %s", __func__, msg);                                    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------------
+struct StageEvent
+{
+    int stage;
+    cudaEvent_t a, b;
+};
+
+struct oibvh_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    bool timing = false;
+    bool capturing = false;
+    uint64_t capture_launches = 0;
+    uint64_t generation = 0; // bumped whenever device buffers referenced by enqueued work are reallocated
+    std::vector<StageEvent> events;
+    float stage_ms[OIBVH_STAGE_COUNT] = {0, 0, 0, 0};
+};
+
+struct oibvh_graph
+{
+    oibvh_ctx* ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+    uint64_t generation = 0;
+};
+
+struct oibvh_tree
+{
+    oibvh_ctx* ctx = nullptr;
+    uint32_t T = 0, V = 0, N = 0, L = 0;
+    MeshAabb mesh;
+    bool built = false;
+    // persistent state
+    float* pos = nullptr;          // V x 3
+    uint32_t* faces_in = nullptr;  // T x 3, input order
+    uint32_t* faces = nullptr;     // T x 3, Morton order
+    float* nodes = nullptr;        // N x 6
+    // sort state: (keys_a, vals_a) hold the sorted keys / permutation after a build
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    uint32_t* sort_ctl = nullptr; // [hist: passes*radix][ticket: passes (padded to 64)][status: passes*tiles*radix]
+    size_t sort_ctl_words = 0;
+    uint32_t* done_counter = nullptr;
+};
+
+struct oibvh_scene
+{
+    oibvh_ctx* ctx = nullptr;
+    std::vector<oibvh_tree*> trees;
+    ObjDesc* d_objs = nullptr;
+    size_t d_objs_cap = 0;
+    bool objs_dirty = true;
+    uint4* front[2] = {nullptr, nullptr};
+    uint4* cand = nullptr;
+    uint4* pairs = nullptr;
+    uint32_t front_cap = 0, cand_cap = 0, pair_cap = 0;
+    uint32_t* counters = nullptr;   // device, CTR_WORDS
+    uint32_t* h_counters = nullptr; // pinned host mirror
+    uint32_t rank = 0, world = 1;
+    uint32_t last_entry = 0, last_expand = 0, last_rounds = 0;
+    bool detect_pending = false;
+    uint32_t hint_front = 0, hint_cand = 0;
+    uint64_t enqueue_generation = 0;
+};
+
+namespace
+{
+
+struct DeviceGuard
+{
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void count_launch(oibvh_ctx* c, uint64_t n = 1)
+{
+    if (c->capturing)
+        c->capture_launches += n;
+    else
+        c->launches += n;
+}
+
+struct StageScope
+{
+    oibvh_ctx* c;
+    int idx = -1;
+    StageScope(oibvh_ctx* ctx, int stage) : c(ctx)
+    {
+        if (!c->timing || c->capturing) return;
+        StageEvent ev{stage, nullptr, nullptr};
+        if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) return;
+        cudaEventRecord(ev.a, c->stream);
+        c->events.push_back(ev);
+        idx = (int)c->events.size() - 1;
+    }
+    ~StageScope()
+    {
+        if (idx >= 0) cudaEventRecord(c->events[idx].b, c->stream);
+    }
+};
+
+template <typename Tp>
+int dev_alloc(Tp** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(Tp)));
+    return OIBVH_OK;
+}
+
+void tree_free(oibvh_tree* t)
+{
+    cudaFree(t->pos);
+    cudaFree(t->faces_in);
+    cudaFree(t->faces);
+    cudaFree(t->nodes);
+    cudaFree(t->keys_a);
+    cudaFree(t->keys_b);
+    cudaFree(t->vals_a);
+    cudaFree(t->vals_b);
+    cudaFree(t->sort_ctl);
+    cudaFree(t->done_counter);
+}
+
+int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6], oibvh_tree** out)
+{
+    oibvh_tree* t = new (std::nothrow) oibvh_tree;
+    if (!t) return fail(OIBVH_ERR_NOMEM, "host allocation failed");
+    t->ctx = ctx;
+    t->T = T;
+    t->V = V;
+    t->L = ceil_log2_u32(T);
+    t->N = tree_size(T);
+    memcpy(t->mesh.v, mesh_aabb, sizeof(float) * 6);
+    const uint32_t tiles = onesweep_tiles(T);
+    const size_t radix = (size_t)1 << kRadixBits;
+    t->sort_ctl_words = kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix;
+    int rc = OIBVH_OK;
+    // round the index buffers up to whole 16-byte groups so that 128-bit accesses of the last group stay in bounds
+    const size_t T4 = ((size_t)T + 3) / 4 * 4;
+    if ((rc = dev_alloc(&t->pos, (size_t)V * 3)) || (rc = dev_alloc(&t->faces_in, T4 * 3)) ||
+        (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
+        (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
+        (rc = dev_alloc(&t->vals_b, T4)) || (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
+        (rc = dev_alloc(&t->done_counter, 1)))
+    {
+        tree_free(t);
+        delete t;
+        return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess)
+    {
+        tree_free(t);
+        delete t;
+        return fail(OIBVH_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return OIBVH_OK;
+}
+
+void scene_free_buffers(oibvh_scene* s)
+{
+    cudaFree(s->front[0]);
+    cudaFree(s->front[1]);
+    cudaFree(s->cand);
+    cudaFree(s->pairs);
+    s->front[0] = s->front[1] = s->cand = s->pairs = nullptr;
+}
+
+int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, uint32_t pair_cap)
+{
+    scene_free_buffers(s);
+    s->ctx->generation++;
+    int rc;
+    if ((rc = dev_alloc(&s->front[0], front_cap)) || (rc = dev_alloc(&s->front[1], front_cap)) ||
+        (rc = dev_alloc(&s->cand, cand_cap)) || (rc = dev_alloc(&s->pairs, pair_cap)))
+        return rc;
+    s->front_cap = front_cap;
+    s->cand_cap = cand_cap;
+    s->pair_cap = pair_cap;
+    return OIBVH_OK;
+}
+
+uint32_t grow_to(uint32_t cap, uint64_t needed)
+{
+    uint64_t n = std::max<uint64_t>((uint64_t)cap * 2, needed + needed / 2 + 1024);
+    n = std::min<uint64_t>(n, 0xfffffff0ull);
+    return (uint32_t)n;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------------
+extern "C" const char* oibvh_last_error(void) { return g_last_error.c_str(); }
+extern "C" int oibvh_version(void) { return 100; }
+extern "C" int oibvh_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx** out)
+{
+    REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(OIBVH_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(OIBVH_ERR_CUDA, "cannot select device %d", device);
+    oibvh_ctx* c = new (std::nothrow) oibvh_ctx;
+    if (!c) return fail(OIBVH_ERR_NOMEM, "host allocation failed");
+    c->device = device;
+    if (use_given)
+    {
+        c->stream = static_cast<cudaStream_t>(stream);
+        c->own_stream = false;
+    }
+    else
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+        {
+            delete c;
+            return fail(OIBVH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    cudaError_t e = tree_emit_configure();
+    if (e != cudaSuccess)
+    {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(OIBVH_ERR_CUDA, "kernel configuration failed (is this an sm_100a device?): %s",
+                    cudaGetErrorString(e));
+    }
+    *out = c;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_create(int device, oibvh_ctx** out) { return ctx_create_impl(device, nullptr, false, out); }
+extern "C" int oibvh_ctx_create_on_stream(int device, void* cuda_stream, oibvh_ctx** out)
+{
+    return ctx_create_impl(device, cuda_stream, true, out);
+}
+
+extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
+{
+    if (!ctx) return OIBVH_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->events)
+    {
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_synchronize(oibvh_ctx* ctx)
+{
+    REQUIRE(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_get_stream(oibvh_ctx* ctx, void** cuda_stream)
+{
+    REQUIRE(ctx && cuda_stream, "NULL argument");
+    *cuda_stream = ctx->stream;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_launch_count(oibvh_ctx* ctx, uint64_t* launches)
+{
+    REQUIRE(ctx && launches, "NULL argument");
+    *launches = ctx->launches;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_enable_timing(oibvh_ctx* ctx, int enable)
+{
+    REQUIRE(ctx != nullptr, "ctx is NULL");
+    ctx->timing = enable != 0;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_stage_ms(oibvh_ctx* ctx, float ms[OIBVH_STAGE_COUNT])
+{
+    REQUIRE(ctx && ms, "NULL argument");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < OIBVH_STAGE_COUNT; i++) ctx->stage_ms[i] = 0.f;
+    for (auto& ev : ctx->events)
+    {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev.a, ev.b) == cudaSuccess) ctx->stage_ms[ev.stage] += t;
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    ctx->events.clear();
+    memcpy(ms, ctx->stage_ms, sizeof(float) * OIBVH_STAGE_COUNT);
+    return OIBVH_OK;
+}
+
+// ---- CUDA-graph capture of whatever the caller enqueues between begin/end (a whole frame, typically) ----
+extern "C" int oibvh_ctx_capture_begin(oibvh_ctx* ctx)
+{
+    REQUIRE(ctx != nullptr, "ctx is NULL");
+    REQUIRE(!ctx->capturing, "capture already in progress");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    ctx->capture_launches = 0;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_ctx_capture_end(oibvh_ctx* ctx, oibvh_graph** out)
+{
+    REQUIRE(ctx && out, "NULL argument");
+    REQUIRE(ctx->capturing, "no capture in progress");
+    DeviceGuard g(ctx->device);
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamEndCapture(ctx->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess)
+    {
+        cudaGraphDestroy(graph);
+        return fail(OIBVH_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    oibvh_graph* gr = new (std::nothrow) oibvh_graph;
+    if (!gr)
+    {
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        return fail(OIBVH_ERR_NOMEM, "host allocation failed");
+    }
+    gr->ctx = ctx;
+    gr->graph = graph;
+    gr->exec = exec;
+    gr->launches = ctx->capture_launches;
+    gr->generation = ctx->generation;
+    *out = gr;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_graph_launch(oibvh_graph* graph)
+{
+    REQUIRE(graph != nullptr, "graph is NULL");
+    oibvh_ctx* ctx = graph->ctx;
+    if (graph->generation != ctx->generation)
+        return fail(OIBVH_ERR_INVALID, "graph is stale: device buffers were reallocated after capture; re-capture");
+    DeviceGuard g(ctx->device);
+    CU(cudaGraphLaunch(graph->exec, ctx->stream));
+    ctx->launches += graph->launches;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_graph_destroy(oibvh_graph* graph)
+{
+    if (!graph) return OIBVH_OK;
+    DeviceGuard g(graph->ctx->device);
+    cudaGraphExecDestroy(graph->exec);
+    cudaGraphDestroy(graph->graph);
+    delete graph;
+    return OIBVH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tree
+// ---------------------------------------------------------------------------------------------------
+static int tree_create_impl(oibvh_ctx* ctx, const float* positions, uint32_t V, const uint32_t* indices, uint32_t T,
+                            const float mesh_aabb[6], bool from_device, oibvh_tree** out)
+{
+    REQUIRE(ctx && positions && indices && mesh_aabb && out, "NULL argument");
+    *out = nullptr;
+    REQUIRE(T >= 2, "a tree needs at least 2 triangles (the reference's schedule underflows for 1)");
+    REQUIRE(T <= (1u << kNodeLevelShift), "too many triangles for one tree (max 2^26)");
+    REQUIRE(V >= 1, "no vertices");
+    if (!from_device)
+    {
+        const size_t n = (size_t)T * 3;
+        uint32_t mx = 0;
+        for (size_t i = 0; i < n; i++) mx = std::max(mx, indices[i]);
+        if (mx >= V) return fail(OIBVH_ERR_INVALID, "triangle index %u out of range (V = %u)", mx, V);
+    }
+    DeviceGuard g(ctx->device);
+    oibvh_tree* t = nullptr;
+    int rc = tree_alloc(ctx, V, T, mesh_aabb, &t);
+    if (rc) return rc;
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMemcpyAsync(t->pos, positions, sizeof(float) * 3 * (size_t)V, kind, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(t->faces_in, indices, sizeof(uint32_t) * 3 * (size_t)T, kind, ctx->stream);
+    if (e == cudaSuccess && !from_device) e = cudaStreamSynchronize(ctx->stream); // caller may free its buffers
+    if (e != cudaSuccess)
+    {
+        tree_free(t);
+        delete t;
+        return fail(OIBVH_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_create(oibvh_ctx* ctx, const float* host_positions, uint32_t V, const uint32_t* host_indices,
+                                 uint32_t T, const float mesh_aabb[6], oibvh_tree** out)
+{
+    return tree_create_impl(ctx, host_positions, V, host_indices, T, mesh_aabb, false, out);
+}
+
+extern "C" int oibvh_tree_create_from_device(oibvh_ctx* ctx, const float* dev_positions, uint32_t V,
+                                             const uint32_t* dev_indices, uint32_t T, const float mesh_aabb[6],
+                                             oibvh_tree** out)
+{
+    return tree_create_impl(ctx, dev_positions, V, dev_indices, T, mesh_aabb, true, out);
+}
+
+extern "C" int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out)
+{
+    REQUIRE(other && out, "NULL argument");
+    *out = nullptr;
+    oibvh_ctx* ctx = other->ctx;
+    DeviceGuard g(ctx->device);
+    oibvh_tree* t = nullptr;
+    int rc = tree_alloc(ctx, other->V, other->T, other->mesh.v, &t);
+    if (rc) return rc;
+    const size_t T = other->T;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](void* d, const void* s, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    };
+    cp(t->pos, other->pos, sizeof(float) * 3 * (size_t)other->V);
+    cp(t->faces_in, other->faces_in, sizeof(uint32_t) * 3 * T);
+    if (other->built)
+    {
+        cp(t->faces, other->faces, sizeof(uint32_t) * 3 * T);
+        cp(t->nodes, other->nodes, sizeof(float) * 6 * (size_t)other->N);
+        cp(t->keys_a, other->keys_a, sizeof(uint32_t) * T);
+        cp(t->vals_a, other->vals_a, sizeof(uint32_t) * T);
+    }
+    if (e != cudaSuccess)
+    {
+        tree_free(t);
+        delete t;
+        return fail(OIBVH_ERR_CUDA, "clone copy failed: %s", cudaGetErrorString(e));
+    }
+    t->built = other->built;
+    *out = t;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_destroy(oibvh_tree* tree)
+{
+    if (!tree) return OIBVH_OK;
+    DeviceGuard g(tree->ctx->device);
+    cudaStreamSynchronize(tree->ctx->stream);
+    tree_free(tree);
+    delete tree;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_positions)
+{
+    REQUIRE(tree && host_positions, "NULL argument");
+    DeviceGuard g(tree->ctx->device);
+    CU(cudaMemcpyAsync(tree->pos, host_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyHostToDevice,
+                       tree->ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const float* dev_positions)
+{
+    REQUIRE(tree && dev_positions, "NULL argument");
+    DeviceGuard g(tree->ctx->device);
+    CU(cudaMemcpyAsync(tree->pos, dev_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToDevice,
+                       tree->ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_transform(oibvh_tree* tree, const float M[16])
+{
+    REQUIRE(tree && M, "NULL argument");
+    DeviceGuard g(tree->ctx->device);
+    Mat4 m;
+    memcpy(m.m, M, sizeof(float) * 16);
+    CU(launch_transform(tree->pos, tree->V, m, tree->ctx->stream));
+    count_launch(tree->ctx);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_build(oibvh_tree* tree)
+{
+    REQUIRE(tree != nullptr, "tree is NULL");
+    oibvh_ctx* ctx = tree->ctx;
+    DeviceGuard g(ctx->device);
+    StageScope scope(ctx, OIBVH_STAGE_BUILD);
+    cudaStream_t s = ctx->stream;
+    const size_t radix = (size_t)1 << kRadixBits;
+    uint32_t* hist = tree->sort_ctl;
+    uint32_t* ticket = tree->sort_ctl + kRadixPasses * radix;
+    uint32_t* status = ticket + 64;
+    CU(cudaMemsetAsync(tree->sort_ctl, 0, tree->sort_ctl_words * sizeof(uint32_t), s));
+    CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, hist, s));
+    count_launch(ctx);
+    uint32_t *kin = tree->keys_a, *kout = tree->keys_b, *vin = nullptr, *vout = tree->vals_b;
+    for (int p = 0; p < kRadixPasses; p++)
+    {
+        CU(launch_onesweep_pass(kin, vin, kout, vout, tree->T, p, hist, status, ticket, s));
+        count_launch(ctx);
+        // ping-pong: after pass p the data is in (kout, vout)
+        uint32_t* nk = kout;
+        uint32_t* nv = vout;
+        kout = (nk == tree->keys_b) ? tree->keys_a : tree->keys_b;
+        vout = (nv == tree->vals_b) ? tree->vals_a : tree->vals_b;
+        kin = nk;
+        vin = nv;
+    }
+    static_assert(kRadixPasses % 2 == 0, "an even number of passes leaves the result in (keys_a, vals_a)");
+    CU(launch_tree_emit(true, tree->faces_in, tree->vals_a, tree->faces, tree->pos, tree->nodes, tree->T,
+                        tree->done_counter, s));
+    count_launch(ctx);
+    tree->built = true;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_refit(oibvh_tree* tree)
+{
+    REQUIRE(tree != nullptr, "tree is NULL");
+    REQUIRE(tree->built, "refit before build");
+    oibvh_ctx* ctx = tree->ctx;
+    DeviceGuard g(ctx->device);
+    StageScope scope(ctx, OIBVH_STAGE_REFIT);
+    CU(launch_tree_emit(false, tree->faces, nullptr, nullptr, tree->pos, tree->nodes, tree->T, tree->done_counter,
+                        ctx->stream));
+    count_launch(ctx);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_get_info(const oibvh_tree* tree, uint32_t* T, uint32_t* V, uint32_t* N, uint32_t* depth)
+{
+    REQUIRE(tree != nullptr, "tree is NULL");
+    if (T) *T = tree->T;
+    if (V) *V = tree->V;
+    if (N) *N = tree->N;
+    if (depth)
+    {
+        // OibvhTree::getDepth() = ilog2(m_aabbTree.size())  (src/cuda/oibvhTree.cu:45-48)
+        uint32_t d = 0;
+        while ((2ull << d) <= tree->N) d++;
+        *depth = d;
+    }
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_is_built(const oibvh_tree* tree, int* built)
+{
+    REQUIRE(tree && built, "NULL argument");
+    *built = tree->built ? 1 : 0;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_download(oibvh_tree* tree, oibvh_aabb* host_nodes, uint32_t* host_sorted_faces,
+                                   uint32_t* host_perm)
+{
+    REQUIRE(tree != nullptr, "tree is NULL");
+    REQUIRE(tree->built, "download before build");
+    oibvh_ctx* ctx = tree->ctx;
+    DeviceGuard g(ctx->device);
+    static_assert(sizeof(oibvh_aabb) == 24, "aabb record is 24 bytes");
+    if (host_nodes)
+        CU(cudaMemcpyAsync(host_nodes, tree->nodes, sizeof(oibvh_aabb) * (size_t)tree->N, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    if (host_sorted_faces)
+        CU(cudaMemcpyAsync(host_sorted_faces, tree->faces, sizeof(uint32_t) * 3 * (size_t)tree->T,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_perm)
+        CU(cudaMemcpyAsync(host_perm, tree->vals_a, sizeof(uint32_t) * (size_t)tree->T, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_download_positions(oibvh_tree* tree, float* host_positions)
+{
+    REQUIRE(tree && host_positions, "NULL argument");
+    DeviceGuard g(tree->ctx->device);
+    CU(cudaMemcpyAsync(host_positions, tree->pos, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToHost,
+                       tree->ctx->stream));
+    CU(cudaStreamSynchronize(tree->ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_download_keys(oibvh_tree* tree, uint32_t* host_sorted_keys)
+{
+    REQUIRE(tree && host_sorted_keys, "NULL argument");
+    REQUIRE(tree->built, "download before build");
+    DeviceGuard g(tree->ctx->device);
+    CU(cudaMemcpyAsync(host_sorted_keys, tree->keys_a, sizeof(uint32_t) * (size_t)tree->T, cudaMemcpyDeviceToHost,
+                       tree->ctx->stream));
+    CU(cudaStreamSynchronize(tree->ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_device_views(oibvh_tree* tree, const oibvh_aabb** dev_nodes,
+                                       const uint32_t** dev_sorted_faces, const float** dev_positions)
+{
+    REQUIRE(tree != nullptr, "tree is NULL");
+    if (dev_nodes) *dev_nodes = reinterpret_cast<const oibvh_aabb*>(tree->nodes);
+    if (dev_sorted_faces) *dev_sorted_faces = tree->faces;
+    if (dev_positions) *dev_positions = tree->pos;
+    return OIBVH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------------
+extern "C" int oibvh_scene_create(oibvh_ctx* ctx, oibvh_scene** out)
+{
+    REQUIRE(ctx && out, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    oibvh_scene* s = new (std::nothrow) oibvh_scene;
+    if (!s) return fail(OIBVH_ERR_NOMEM, "host allocation failed");
+    s->ctx = ctx;
+    int rc = dev_alloc(&s->counters, (size_t)CTR_WORDS);
+    if (rc)
+    {
+        delete s;
+        return rc;
+    }
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&s->h_counters), sizeof(uint32_t) * CTR_WORDS);
+    if (e != cudaSuccess)
+    {
+        cudaFree(s->counters);
+        delete s;
+        return fail(OIBVH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
+    }
+    memset(s->h_counters, 0, sizeof(uint32_t) * CTR_WORDS);
+    *out = s;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_destroy(oibvh_scene* scene)
+{
+    if (!scene) return OIBVH_OK;
+    DeviceGuard g(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
+    scene_free_buffers(scene);
+    cudaFree(scene->d_objs);
+    cudaFree(scene->counters);
+    cudaFreeHost(scene->h_counters);
+    delete scene;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_add_tree(oibvh_scene* scene, oibvh_tree* tree)
+{
+    REQUIRE(scene && tree, "NULL argument");
+    REQUIRE(tree->built, "tree must be built before it is added (Scene::addOibvhTree asserts m_buildDone)");
+    REQUIRE(tree->ctx == scene->ctx, "tree and scene belong to different contexts");
+    scene->trees.push_back(tree);
+    scene->objs_dirty = true;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    REQUIRE(world >= 1 && rank < world, "need rank < world");
+    scene->rank = rank;
+    scene->world = world;
+    return OIBVH_OK;
+}
+
+static int scene_upload_objs(oibvh_scene* s)
+{
+    if (!s->objs_dirty) return OIBVH_OK;
+    oibvh_ctx* ctx = s->ctx;
+    const size_t n = s->trees.size();
+    if (n > s->d_objs_cap)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(s->d_objs);
+        s->d_objs = nullptr;
+        ctx->generation++;
+        int rc = dev_alloc(&s->d_objs, n);
+        if (rc) return rc;
+        s->d_objs_cap = n;
+    }
+    std::vector<ObjDesc> h(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        const oibvh_tree* t = s->trees[i];
+        h[i].nodes = t->nodes;
+        h[i].faces = t->faces;
+        h[i].pos = t->pos;
+        h[i].T = t->T;
+        h[i].L = t->L;
+    }
+    CU(cudaMemcpyAsync(s->d_objs, h.data(), sizeof(ObjDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
+    s->objs_dirty = false;
+    return OIBVH_OK;
+}
+
+static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_levels)
+{
+    oibvh_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_obj = (uint32_t)s->trees.size();
+    uint32_t maxL = 0;
+    for (auto* t : s->trees) maxL = std::max(maxL, t->L);
+    if (expand_levels == 0) expand_levels = (s->hint_front > (1u << 18)) ? 1u : 3u; // small fronts are latency-bound
+    expand_levels = std::min(expand_levels, 8u);
+    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 12u) : expand_levels;
+    const uint32_t reached = std::min(k0, maxL);
+    const uint32_t rounds = 2 + (maxL - reached + expand_levels - 1) / expand_levels; // root round + ... + leaf round
+    if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
+
+    CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));
+    {
+        StageScope scope(ctx, OIBVH_STAGE_BROAD);
+        CU(launch_seed(n_obj, s->front[0], s->front_cap, s->counters, st));
+        count_launch(ctx);
+        const uint32_t hint = std::max(s->hint_front, 1u << 14);
+        for (uint32_t r = 0; r < rounds; r++)
+        {
+            CU(launch_expand(s->d_objs, s->front[r & 1], s->front[(r + 1) & 1], s->front_cap, s->cand, s->cand_cap,
+                             s->counters, r, r == 0 ? k0 : expand_levels, s->rank, s->world, hint, st));
+            count_launch(ctx);
+        }
+    }
+    {
+        StageScope scope(ctx, OIBVH_STAGE_NARROW);
+        CU(launch_narrow(s->d_objs, s->cand, s->cand_cap, s->pairs, s->pair_cap, s->counters,
+                         std::max(s->hint_cand, 1u << 14), st));
+        count_launch(ctx);
+    }
+    CU(cudaMemcpyAsync(s->h_counters, s->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost, st));
+    s->last_entry = entry_level;
+    s->last_expand = expand_levels;
+    s->last_rounds = rounds;
+    s->detect_pending = true;
+    s->enqueue_generation = ctx->generation;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_detect_async(oibvh_scene* scene, uint32_t entry_level, uint32_t expand_levels)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    REQUIRE(scene->trees.size() >= 1, "empty scene");
+    oibvh_ctx* ctx = scene->ctx;
+    DeviceGuard g(ctx->device);
+    if (ctx->capturing)
+    {
+        REQUIRE(!scene->objs_dirty && scene->front_cap > 0, "run one detection before capturing a graph");
+    }
+    else
+    {
+        int rc = scene_upload_objs(scene);
+        if (rc) return rc;
+        if (scene->front_cap == 0)
+        {
+            rc = scene_alloc_buffers(scene, 1u << 20, 1u << 20, 1u << 19);
+            if (rc) return rc;
+        }
+    }
+    if (scene->trees.size() < 2)
+    {
+        // a single object has no pairs i<j (the reference loops over i<j only, scene.cu:195-196)
+        CU(cudaMemsetAsync(scene->counters, 0, sizeof(uint32_t) * CTR_WORDS, ctx->stream));
+        CU(cudaMemcpyAsync(scene->h_counters, scene->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        scene->detect_pending = true;
+        scene->last_rounds = 0;
+        return OIBVH_OK;
+    }
+    return scene_enqueue(scene, entry_level, expand_levels);
+}
+
+extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_candidates)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    oibvh_ctx* ctx = scene->ctx;
+    DeviceGuard g(ctx->device);
+    for (int attempt = 0; attempt < 12; attempt++)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        const uint32_t* h = scene->h_counters;
+        uint32_t max_front = 0;
+        for (uint32_t r = 0; r <= scene->last_rounds; r++) max_front = std::max(max_front, h[CTR_FRONT0 + r]);
+        scene->hint_front = max_front;
+        scene->hint_cand = h[CTR_CANDIDATES];
+        if (h[CTR_OVERFLOW] == 0)
+        {
+            if (n_pairs) *n_pairs = h[CTR_PAIRS];
+            if (n_candidates) *n_candidates = h[CTR_CANDIDATES];
+            scene->detect_pending = false;
+            return OIBVH_OK;
+        }
+        // a queue overflowed: grow (counts keep counting past the capacity, so they are lower bounds) and redo
+        uint32_t fc = scene->front_cap, cc = scene->cand_cap, pc = scene->pair_cap;
+        if (h[CTR_OVERFLOW] & 1u) fc = grow_to(fc, max_front);
+        if (h[CTR_OVERFLOW] & 2u) cc = grow_to(cc, h[CTR_CANDIDATES]);
+        if (h[CTR_OVERFLOW] & 4u) pc = grow_to(pc, h[CTR_PAIRS]);
+        if (fc == scene->front_cap && cc == scene->cand_cap && pc == scene->pair_cap)
+            return fail(OIBVH_ERR_OVERFLOW, "work queues cannot grow further");
+        int rc = scene_alloc_buffers(scene, fc, cc, pc);
+        if (rc) return rc;
+        rc = scene_enqueue(scene, scene->last_entry, scene->last_expand);
+        if (rc) return rc;
+    }
+    return fail(OIBVH_ERR_OVERFLOW, "work queues still overflow after repeated growth");
+}
+
+extern "C" int oibvh_scene_detect(oibvh_scene* scene, uint32_t entry_level, uint32_t expand_levels, uint32_t* n_pairs,
+                                  uint32_t* n_candidates)
+{
+    int rc = oibvh_scene_detect_async(scene, entry_level, expand_levels);
+    if (rc) return rc;
+    return oibvh_scene_get_counts(scene, n_pairs, n_candidates);
+}
+
+extern "C" int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    uint32_t n = 0;
+    int rc = oibvh_scene_get_counts(scene, &n, nullptr);
+    if (rc) return rc;
+    if (n == 0) return OIBVH_OK;
+    REQUIRE(host_pairs != nullptr, "host_pairs is NULL");
+    DeviceGuard g(scene->ctx->device);
+    static_assert(sizeof(oibvh_int_tri_pair) == sizeof(uint4), "pair record is 16 bytes");
+    CU(cudaMemcpyAsync(host_pairs, scene->pairs, sizeof(oibvh_int_tri_pair) * (size_t)n, cudaMemcpyDeviceToHost,
+                       scene->ctx->stream));
+    CU(cudaStreamSynchronize(scene->ctx->stream));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs)
+{
+    REQUIRE(scene && dev_pairs && n_pairs, "NULL argument");
+    int rc = oibvh_scene_get_counts(scene, n_pairs, nullptr);
+    if (rc) return rc;
+    *dev_pairs = reinterpret_cast<const oibvh_int_tri_pair*>(scene->pairs);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds,
+                                           uint32_t* n_rounds)
+{
+    REQUIRE(scene && tested && n_rounds, "NULL argument");
+    int rc = oibvh_scene_get_counts(scene, nullptr, nullptr);
+    if (rc) return rc;
+    const uint32_t n = std::min(max_rounds, scene->last_rounds);
+    for (uint32_t r = 0; r < n; r++) tested[r] = scene->h_counters[CTR_FRONT0 + r];
+    *n_rounds = n;
+    return OIBVH_OK;
+}
