@@ -159,6 +159,11 @@ int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_ca
 int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs);
 /* device view of the pair list of the last detection (for a collective gather by the caller) */
 int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs);
+/* device view of the counter block of the last detection: word 0 = candidates, word 1 = pairs (lets a caller chain
+ * a collective on the stream without a host round trip). Does not synchronise. */
+int oibvh_scene_device_counters(oibvh_scene* scene, const uint32_t** dev_counters);
+/* current capacity (records) of the device pair list returned by oibvh_scene_device_pairs */
+int oibvh_scene_pair_capacity(oibvh_scene* scene, uint32_t* capacity);
 /* per-round BVTT statistics of the last detection: tested[r] nodes were overlap-tested in round r.
  * Returns the number of rounds written (<= max_rounds). */
 int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds, uint32_t* n_rounds);

@@ -85,6 +85,8 @@ _SIGNATURES = {
     "oibvh_scene_get_counts": (C.c_int, [_vp, _u32p, _u32p]),
     "oibvh_scene_get_pairs": (C.c_int, [_vp, _vp]),
     "oibvh_scene_device_pairs": (C.c_int, [_vp, C.POINTER(_vp), _u32p]),
+    "oibvh_scene_device_counters": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "oibvh_scene_pair_capacity": (C.c_int, [_vp, _u32p]),
     "oibvh_scene_get_round_stats": (C.c_int, [_vp, _u32p, _u32, _u32p]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
@@ -416,6 +418,10 @@ class OibvhTree:
         _check(_lib.oibvh_tree_set_positions(self._h, _ptr(p)))
         self._keep = p  # async H2D from pageable memory is staged by the runtime, but keep a ref anyway
 
+    def set_positions_from_host_ptr(self, host_ptr):
+        """raw host pointer (e.g. a pinned torch tensor's data_ptr()); the caller keeps it alive until the next sync"""
+        _check(_lib.oibvh_tree_set_positions(self._h, _vp(int(host_ptr))))
+
     def set_positions_from_device(self, dev_ptr):
         _check(_lib.oibvh_tree_set_positions_from_device(self._h, _vp(int(dev_ptr))))
 
@@ -550,6 +556,16 @@ class Scene:
         p, n = _vp(), _u32()
         _check(_lib.oibvh_scene_device_pairs(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def device_counters(self):
+        p = _vp()
+        _check(_lib.oibvh_scene_device_counters(self._h, C.byref(p)))
+        return p.value
+
+    def pair_capacity(self):
+        n = _u32()
+        _check(_lib.oibvh_scene_pair_capacity(self._h, C.byref(n)))
+        return n.value
 
     def round_stats(self):
         buf = (C.c_uint32 * 64)()

@@ -924,6 +924,20 @@ extern "C" int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_
     return OIBVH_OK;
 }
 
+extern "C" int oibvh_scene_device_counters(oibvh_scene* scene, const uint32_t** dev_counters)
+{
+    REQUIRE(scene && dev_counters, "NULL argument");
+    *dev_counters = scene->counters;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_pair_capacity(oibvh_scene* scene, uint32_t* capacity)
+{
+    REQUIRE(scene && capacity, "NULL argument");
+    *capacity = scene->pair_cap;
+    return OIBVH_OK;
+}
+
 extern "C" int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds,
                                            uint32_t* n_rounds)
 {

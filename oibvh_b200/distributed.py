@@ -1,0 +1,41 @@
+"""Multi-GPU plumbing: one process per GPU, the BVH replicated, the BVTT seed front sharded
+(oibvh_scene_set_shard), and only the pair list exchanged.
+
+`torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests) carries the single exchange step of the
+path: an all-gather of the per-rank pair counts followed by an all-gather of the 16-byte pair records padded
+to the largest shard. Messages are KB-MB, i.e. latency-bound; nothing else crosses GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+
+def gather_pairs(local_pairs, n_local, group=None):
+    """local_pairs: int32 tensor [cap>=n_local, 4] on this rank's device (rows beyond n_local are ignored).
+    Returns the concatenation over ranks ([sum n, 4], rank order) on every rank."""
+    world = dist.get_world_size(group)
+    dev = local_pairs.device
+    cnt = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    send = torch.zeros((width, 4), dtype=torch.int32, device=dev)
+    if n_local:
+        send[:n_local] = local_pairs[:n_local]
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return torch.cat([recv[r][:counts[r]] for r in range(world)], dim=0)
+
+
+def pairs_tensor_from_device_ptr(ptr, n, device):
+    """zero-copy int32 [n,4] view of the scene's device pair list (oibvh_scene_device_pairs)"""
+    if n == 0:
+        return torch.empty((0, 4), dtype=torch.int32, device=device)
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(n), 4), "typestr": "<i4", "data": (int(ptr), False), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(h, device=device)

@@ -1,0 +1,197 @@
+"""GPU parity, broad + narrow phase: colliding-pair SETS bit-exact after canonical sorting."""
+import numpy as np
+import pytest
+
+import oibvh_b200 as ob
+import oracle
+from oibvh_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+
+
+def make_scene(ctx, meshes):
+    """meshes: list of (pos, faces) already in world space"""
+    trees = []
+    sc = ob.Scene(ctx)
+    for pos, faces in meshes:
+        t = ob.OibvhTree(ob.Mesh(pos, faces), ctx=ctx)
+        t.build()
+        sc.addOibvhTree(t)
+        trees.append(t)
+    return sc, trees
+
+
+def oracle_pairs(port, meshes):
+    built = [port.build(p, f) for p, f in meshes]
+    pairs, ncand = port.detect([(b["nodes"], b["faces"], p) for b, (p, f) in zip(built, meshes)])
+    return oracle.canonical_pairs(pairs, [b["perm"] for b in built]), ncand
+
+
+def test_golden_two_spheres(ctx, golden):
+    """known answers frozen from the reference's SimpleCollide (and SURVEY.md Appendix A: 456 pairs at n=64)"""
+    g = golden["collide"]
+    for n in (16, 64):
+        pos, faces, posB, want = (g[f"sphere{n}_{k}"] for k in ("pos", "faces", "posB", "pairs"))
+        sc, _ = make_scene(ctx, [(pos, faces), (posB, faces)])
+        sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+        assert sc.getIntTriPairCount() == len(want)
+        assert np.array_equal(sc.canonical_pairs(), want)
+    assert sc.getIntTriPairCount() == 456 and sc.getCandidateCount() == 2093
+
+
+def test_golden_three_bodies(ctx, golden):
+    g = golden["collide"]
+    meshes = [(g[f"body{k}_pos"], g[f"body{k}_faces"]) for k in range(3)]
+    sc, _ = make_scene(ctx, meshes)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    assert np.array_equal(sc.canonical_pairs(), g["bodies_pairs"])
+    raw = sc.m_intTriPairs
+    assert (raw[:, 0] < raw[:, 1]).all()  # bvhIndex[0] < bvhIndex[1]  (scene.cu:195-196)
+    assert len(np.unique(raw, axis=0)) == len(raw)  # no duplicates
+
+
+@pytest.mark.parametrize("entry,expand", [(4, 3), (0, 1), (0, 0), (1, 1), (2, 2), (7, 1), (12, 4), (30, 8)])
+def test_pair_set_independent_of_entry_and_expand(ctx, port, entry, expand):
+    pos, faces = meshgen.blob(72, 50, seed=3)
+    faces = meshgen.shuffle_faces(faces)[:7001]
+    posB = port.transform_positions(pos, ob.mat_translate(ob.mat_identity(), (0.8, 0.15, -0.1)))
+    meshes = [(pos, faces), (posB, faces[:4099])]  # different depths: L = 13 and 13 / T not power of two
+    want, ncand = oracle_pairs(port, meshes)
+    sc, _ = make_scene(ctx, meshes)
+    sc.detectCollision(ob.DeviceType.GPU0, entry, expand)
+    assert sc.getCandidateCount() == ncand
+    assert np.array_equal(sc.canonical_pairs(), want)
+    assert len(want) > 50
+
+
+def test_different_depths_and_tiny_trees(ctx, port):
+    big = meshgen.blob(128, 96, seed=4)
+    tiny = meshgen.cube(0.3, (0.9, 0.1, 0.0))
+    two = (tiny[0], tiny[1][:2])  # T = 2, the minimum
+    three = (meshgen.cube(0.25, (-0.8, 0.3, 0.2))[0], meshgen.cube()[1][:3])
+    meshes = [big, tiny, two, three]
+    want, ncand = oracle_pairs(port, meshes)
+    sc, _ = make_scene(ctx, meshes)
+    for entry, expand in [(4, 3), (0, 1)]:
+        sc.detectCollision(ob.DeviceType.GPU0, entry, expand)
+        assert sc.getCandidateCount() == ncand
+        assert np.array_equal(sc.canonical_pairs(), want)
+    assert len(want) > 0
+
+
+def test_no_contact_and_single_object(ctx):
+    a = meshgen.icosphere(2)
+    b = meshgen.icosphere(2, center=(5.0, 0, 0))
+    sc, _ = make_scene(ctx, [a, b])
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    assert sc.getIntTriPairCount() == 0 and sc.m_intTriPairs.shape == (0, 4)
+    sc1, _ = make_scene(ctx, [a])
+    sc1.detectCollision()
+    assert sc1.getIntTriPairCount() == 0
+
+
+def test_touching_and_degenerate_triangles(ctx, port):
+    """identical meshes in place: every shared vertex / edge / coincident triangle is a touching case where an
+    FMA-contracted SAT can flip; UV-sphere poles add zero-area triangles"""
+    pos, faces = meshgen.uv_sphere(24)
+    meshes = [(pos, faces), (pos.copy(), faces.copy())]
+    want, ncand = oracle_pairs(port, meshes)
+    sc, _ = make_scene(ctx, meshes)
+    sc.detectCollision(ob.DeviceType.GPU0, 3, 2)
+    assert sc.getCandidateCount() == ncand
+    assert np.array_equal(sc.canonical_pairs(), want)
+    assert len(want) > len(faces)
+
+
+def test_refit_between_detections_is_honoured(ctx, port):
+    """scene.cu:264-268 re-reads every tree on each detectCollision; here trees are referenced, so a refit shows"""
+    pos, faces = meshgen.blob(60, 40, seed=7)
+    mA, mB = ob.Mesh(pos, faces), ob.Mesh(pos, faces)
+    tA = ob.OibvhTree(mA, ctx=ctx)
+    tA.build()
+    tB = ob.OibvhTree(tA, mB)
+    sc = ob.Scene(ctx)
+    sc.addOibvhTree(tA)
+    sc.addOibvhTree(tB)
+    oa = port.build(pos, faces, mA.m_aabb)
+    counts = []
+    for frame in range(4):
+        mB.rotateX(1.0)  # main.cpp:248-252
+        mB.translate((0.3, 0.0, 0.0))
+        tB.refit()
+        sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+        nodesB = port.refit(mB.m_positions, oa["faces"])
+        pp, _ = port.detect([(oa["nodes"], oa["faces"], pos), (nodesB, oa["faces"], mB.m_positions)])
+        want = oracle.canonical_pairs(pp, [oa["perm"], oa["perm"]])
+        assert np.array_equal(sc.canonical_pairs(), want), f"frame {frame}"
+        counts.append(len(want))
+    assert len(set(counts)) > 1
+
+
+def test_queue_growth_on_overflow(ctx, port):
+    """a dense contact (coincident meshes) overflows the initial 1M-entry queues: they must regrow, not drop"""
+    pos, faces = meshgen.blob(200, 128, seed=9)
+    meshes = [(pos, faces), (pos.copy(), faces.copy())]
+    sc, _ = make_scene(ctx, meshes)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    want, ncand = oracle_pairs(port, meshes)
+    assert sc.getCandidateCount() == ncand
+    assert np.array_equal(sc.canonical_pairs(), want)
+
+
+def test_shards_partition_the_pair_set(ctx, port):
+    pos, faces = meshgen.blob(80, 64, seed=10)
+    posB = port.transform_positions(pos, ob.mat_translate(ob.mat_identity(), (0.7, 0.2, 0.1)))
+    meshes = [(pos, faces), (posB, faces)]
+    want, _ = oracle_pairs(port, meshes)
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            sc, _ = make_scene(ctx, meshes)
+            sc.set_shard(rank, world)
+            sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+            parts.append(sc.canonical_pairs())
+        allp = np.concatenate(parts)
+        assert len(allp) == len(want), f"world={world}: shards overlap or miss pairs"
+        allp = allp[np.lexsort((allp[:, 3], allp[:, 2], allp[:, 1], allp[:, 0]))]
+        assert np.array_equal(allp, want)
+        assert sum(len(p) > 0 for p in parts) >= 2
+
+
+def test_graph_replay_of_a_whole_frame(ctx, port):
+    pos, faces = meshgen.blob(64, 64, seed=12)
+    mA, mB = ob.Mesh(pos, faces), ob.Mesh(pos, faces)
+    tA = ob.OibvhTree(mA, ctx=ctx)
+    tA.build()
+    tB = ob.OibvhTree(tA, mB)
+    M = mB.transform_matrix_rotate((0, 0, 1), 2.0)
+    T2 = mB.transform_matrix_translate((0.25, 0.0, 0.0))
+    sc = ob.Scene(ctx)
+    sc.addOibvhTree(tA)
+    sc.addOibvhTree(tB)
+
+    def frame():
+        tA.build()
+        tB.transform(M)
+        tB.transform(T2)
+        tB.refit(upload=False)
+        sc.detect_async(4, 3)
+
+    frame()
+    sc.counts()  # warm-up: buffers exist
+    before = ctx.launch_count()
+    ctx.capture_begin()
+    frame()
+    graph = ctx.capture_end()
+    assert ctx.launch_count() == before  # capture does not execute
+    oa = port.build(pos, faces, mA.m_aabb)
+    posB = port.transform_positions(port.transform_positions(pos, M), T2)
+    for it in range(3):
+        graph.launch()
+        n, c = sc.counts()
+        posB = port.transform_positions(port.transform_positions(posB, M), T2)
+        nodesB = port.refit(posB, oa["faces"])
+        pp, nc = port.detect([(oa["nodes"], oa["faces"], pos), (nodesB, oa["faces"], posB)])
+        assert (n, c) == (len(pp), nc), f"replay {it}"
+        assert np.array_equal(sc.canonical_pairs(), oracle.canonical_pairs(pp, [oa["perm"], oa["perm"]]))
+    assert ctx.launch_count() > before
