@@ -134,7 +134,8 @@ int oibvh_tree_download(oibvh_tree* tree, oibvh_aabb* host_nodes, uint32_t* host
 int oibvh_tree_download_positions(oibvh_tree* tree, float* host_positions);
 /* sorted 30-bit Morton keys [T] of the last build (debug / parity) */
 int oibvh_tree_download_keys(oibvh_tree* tree, uint32_t* host_sorted_keys);
-/* device views for zero-copy consumers (valid until the tree is destroyed) */
+/* device views for zero-copy consumers (valid until the tree is destroyed). Positions are stored on the device as
+ * 16-byte records (x, y, z, 1) -- V x 4 floats -- so that a gathered vertex is one 128-bit load. */
 int oibvh_tree_device_views(oibvh_tree* tree, const oibvh_aabb** dev_nodes, const uint32_t** dev_sorted_faces,
                             const float** dev_positions);
 
@@ -159,6 +160,10 @@ int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_ca
 int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs);
 /* device view of the pair list of the last detection (for a collective gather by the caller) */
 int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs);
+/* SM-clock cycles CTA 0 of the detection kernel spent in each phase of the last detection: [0] seeding, [1..R]
+ * the R expansion rounds that ran, [R+1] the barrier before the narrow phase, [R+2] its share of the narrow phase.
+ * Returns the number of phases written. Replaces the reference's per-launch stopwatch (scene.cu:299-302, 419). */
+int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases, uint32_t* n_phases);
 /* device view of the counter block of the last detection: word 0 = candidates, word 1 = pairs (lets a caller chain
  * a collective on the stream without a host round trip). Does not synchronise. */
 int oibvh_scene_device_counters(oibvh_scene* scene, const uint32_t** dev_counters);

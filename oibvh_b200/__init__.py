@@ -85,6 +85,7 @@ _SIGNATURES = {
     "oibvh_scene_get_counts": (C.c_int, [_vp, _u32p, _u32p]),
     "oibvh_scene_get_pairs": (C.c_int, [_vp, _vp]),
     "oibvh_scene_device_pairs": (C.c_int, [_vp, C.POINTER(_vp), _u32p]),
+    "oibvh_scene_get_phase_cycles": (C.c_int, [_vp, _u32p, _u32, _u32p]),
     "oibvh_scene_device_counters": (C.c_int, [_vp, C.POINTER(_vp)]),
     "oibvh_scene_pair_capacity": (C.c_int, [_vp, _u32p]),
     "oibvh_scene_get_round_stats": (C.c_int, [_vp, _u32p, _u32, _u32p]),
@@ -556,6 +557,12 @@ class Scene:
         p, n = _vp(), _u32()
         _check(_lib.oibvh_scene_device_pairs(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def phase_cycles(self):
+        buf = (C.c_uint32 * 64)()
+        n = _u32()
+        _check(_lib.oibvh_scene_get_phase_cycles(self._h, buf, 64, C.byref(n)))
+        return [int(buf[i]) for i in range(n.value)]
 
     def device_counters(self):
         p = _vp()

@@ -63,6 +63,7 @@ struct oibvh_ctx
     bool timing = false;
     bool capturing = false;
     uint64_t capture_launches = 0;
+    int collide_grid = 0;    // CTAs of the persistent detection kernel (cooperative launch)
     uint64_t generation = 0; // bumped whenever device buffers referenced by enqueued work are reallocated
     std::vector<StageEvent> events;
     float stage_ms[OIBVH_STAGE_COUNT] = {0, 0, 0, 0};
@@ -84,8 +85,9 @@ struct oibvh_tree
     MeshAabb mesh;
     bool built = false;
     // persistent state
-    float* pos = nullptr;          // V x 3
-    uint32_t* faces_in = nullptr;  // T x 3, input order
+    float4* pos = nullptr;         // V x (x, y, z, 1): one 128-bit load per gathered vertex
+    float* pos_stage = nullptr;    // V x 3 packed: landing / take-off buffer for host transfers
+    uint4* faces_in = nullptr;     // T x (i0, i1, i2, 0), input order
     uint32_t* faces = nullptr;     // T x 3, Morton order
     float* nodes = nullptr;        // N x 6
     // sort state: (keys_a, vals_a) hold the sorted keys / permutation after a build
@@ -172,6 +174,7 @@ int dev_alloc(Tp** p, size_t count)
 void tree_free(oibvh_tree* t)
 {
     cudaFree(t->pos);
+    cudaFree(t->pos_stage);
     cudaFree(t->faces_in);
     cudaFree(t->faces);
     cudaFree(t->nodes);
@@ -195,11 +198,13 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
     memcpy(t->mesh.v, mesh_aabb, sizeof(float) * 6);
     const uint32_t tiles = onesweep_tiles(T);
     const size_t radix = (size_t)1 << kRadixBits;
-    t->sort_ctl_words = kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix;
+    t->sort_ctl_words = std::max(kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix,
+                                 coop_sort_ctl_words());
     int rc = OIBVH_OK;
     // round the index buffers up to whole 16-byte groups so that 128-bit accesses of the last group stay in bounds
     const size_t T4 = ((size_t)T + 3) / 4 * 4;
-    if ((rc = dev_alloc(&t->pos, (size_t)V * 3)) || (rc = dev_alloc(&t->faces_in, T4 * 3)) ||
+    if ((rc = dev_alloc(&t->pos, (size_t)V)) || (rc = dev_alloc(&t->pos_stage, (size_t)V * 3)) ||
+        (rc = dev_alloc(&t->faces_in, T4)) ||
         (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
         (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
         (rc = dev_alloc(&t->vals_b, T4)) || (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
@@ -299,6 +304,8 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
         c->own_stream = true;
     }
     cudaError_t e = tree_emit_configure();
+    if (e == cudaSuccess) e = collide_configure(&c->collide_grid);
+    if (e == cudaSuccess) e = coop_sort_configure();
     if (e != cudaSuccess)
     {
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -465,11 +472,29 @@ static int tree_create_impl(oibvh_ctx* ctx, const float* positions, uint32_t V, 
     oibvh_tree* t = nullptr;
     int rc = tree_alloc(ctx, V, T, mesh_aabb, &t);
     if (rc) return rc;
-    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    cudaError_t e = cudaMemcpyAsync(t->pos, positions, sizeof(float) * 3 * (size_t)V, kind, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(t->faces_in, indices, sizeof(uint32_t) * 3 * (size_t)T, kind, ctx->stream);
-    if (e == cudaSuccess && !from_device) e = cudaStreamSynchronize(ctx->stream); // caller may free its buffers
+    // packed triples arrive (H2D, or straight from the caller's device buffers) and are widened to 16-byte records
+    cudaError_t e = cudaSuccess;
+    uint32_t* faces_stage = nullptr;
+    if (from_device)
+    {
+        e = launch_pack_positions(positions, t->pos, V, ctx->stream);
+        if (e == cudaSuccess) e = launch_pack_faces(indices, t->faces_in, T, ctx->stream);
+    }
+    else
+    {
+        e = cudaMalloc(reinterpret_cast<void**>(&faces_stage), sizeof(uint32_t) * 3 * (size_t)T);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(t->pos_stage, positions, sizeof(float) * 3 * (size_t)V, cudaMemcpyHostToDevice,
+                                ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(faces_stage, indices, sizeof(uint32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice,
+                                ctx->stream);
+        if (e == cudaSuccess) e = launch_pack_positions(t->pos_stage, t->pos, V, ctx->stream);
+        if (e == cudaSuccess) e = launch_pack_faces(faces_stage, t->faces_in, T, ctx->stream);
+    }
+    count_launch(ctx, 2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // caller may free its buffers
+    cudaFree(faces_stage);
     if (e != cudaSuccess)
     {
         tree_free(t);
@@ -507,8 +532,8 @@ extern "C" int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out)
     auto cp = [&](void* d, const void* s, size_t bytes) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
     };
-    cp(t->pos, other->pos, sizeof(float) * 3 * (size_t)other->V);
-    cp(t->faces_in, other->faces_in, sizeof(uint32_t) * 3 * T);
+    cp(t->pos, other->pos, sizeof(float4) * (size_t)other->V);
+    cp(t->faces_in, other->faces_in, sizeof(uint4) * T);
     if (other->built)
     {
         cp(t->faces, other->faces, sizeof(uint32_t) * 3 * T);
@@ -541,8 +566,10 @@ extern "C" int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_posi
 {
     REQUIRE(tree && host_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
-    CU(cudaMemcpyAsync(tree->pos, host_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyHostToDevice,
+    CU(cudaMemcpyAsync(tree->pos_stage, host_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyHostToDevice,
                        tree->ctx->stream));
+    CU(launch_pack_positions(tree->pos_stage, tree->pos, tree->V, tree->ctx->stream));
+    count_launch(tree->ctx);
     return OIBVH_OK;
 }
 
@@ -550,8 +577,8 @@ extern "C" int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const floa
 {
     REQUIRE(tree && dev_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
-    CU(cudaMemcpyAsync(tree->pos, dev_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToDevice,
-                       tree->ctx->stream));
+    CU(launch_pack_positions(dev_positions, tree->pos, tree->V, tree->ctx->stream));
+    count_launch(tree->ctx);
     return OIBVH_OK;
 }
 
@@ -577,21 +604,34 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     uint32_t* hist = tree->sort_ctl;
     uint32_t* ticket = tree->sort_ctl + kRadixPasses * radix;
     uint32_t* status = ticket + 64;
-    CU(cudaMemsetAsync(tree->sort_ctl, 0, tree->sort_ctl_words * sizeof(uint32_t), s));
-    CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, hist, s));
-    count_launch(ctx);
-    uint32_t *kin = tree->keys_a, *kout = tree->keys_b, *vin = nullptr, *vout = tree->vals_b;
-    for (int p = 0; p < kRadixPasses; p++)
+    if (tree->T <= coop_sort_capacity())
     {
-        CU(launch_onesweep_pass(kin, vin, kout, vout, tree->T, p, hist, status, ticket, s));
+        // single-wave size: keys, then all radix passes in one cooperative launch
+        CU(cudaMemsetAsync(tree->sort_ctl, 0, 64 * sizeof(uint32_t), s));
+        CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
         count_launch(ctx);
-        // ping-pong: after pass p the data is in (kout, vout)
-        uint32_t* nk = kout;
-        uint32_t* nv = vout;
-        kout = (nk == tree->keys_b) ? tree->keys_a : tree->keys_b;
-        vout = (nv == tree->vals_b) ? tree->vals_a : tree->vals_b;
-        kin = nk;
-        vin = nv;
+        CU(launch_coop_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->sort_ctl, s));
+        count_launch(ctx);
+    }
+    else
+    {
+        // streaming size: keys + digit histograms, then one onesweep launch per digit
+        CU(cudaMemsetAsync(tree->sort_ctl, 0, tree->sort_ctl_words * sizeof(uint32_t), s));
+        CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, hist, s));
+        count_launch(ctx);
+        uint32_t *kin = tree->keys_a, *kout = tree->keys_b, *vin = nullptr, *vout = tree->vals_b;
+        for (int p = 0; p < kRadixPasses; p++)
+        {
+            CU(launch_onesweep_pass(kin, vin, kout, vout, tree->T, p, hist, status, ticket, s));
+            count_launch(ctx);
+            // ping-pong: after pass p the data is in (kout, vout)
+            uint32_t* nk = kout;
+            uint32_t* nv = vout;
+            kout = (nk == tree->keys_b) ? tree->keys_a : tree->keys_b;
+            vout = (nv == tree->vals_b) ? tree->vals_a : tree->vals_b;
+            kin = nk;
+            vin = nv;
+        }
     }
     static_assert(kRadixPasses % 2 == 0, "an even number of passes leaves the result in (keys_a, vals_a)");
     CU(launch_tree_emit(true, tree->faces_in, tree->vals_a, tree->faces, tree->pos, tree->nodes, tree->T,
@@ -608,7 +648,7 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
     oibvh_ctx* ctx = tree->ctx;
     DeviceGuard g(ctx->device);
     StageScope scope(ctx, OIBVH_STAGE_REFIT);
-    CU(launch_tree_emit(false, tree->faces, nullptr, nullptr, tree->pos, tree->nodes, tree->T, tree->done_counter,
+    CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
                         ctx->stream));
     count_launch(ctx);
     return OIBVH_OK;
@@ -662,7 +702,9 @@ extern "C" int oibvh_tree_download_positions(oibvh_tree* tree, float* host_posit
 {
     REQUIRE(tree && host_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
-    CU(cudaMemcpyAsync(host_positions, tree->pos, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToHost,
+    CU(launch_unpack_positions(tree->pos, tree->pos_stage, tree->V, tree->ctx->stream));
+    count_launch(tree->ctx);
+    CU(cudaMemcpyAsync(host_positions, tree->pos_stage, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToHost,
                        tree->ctx->stream));
     CU(cudaStreamSynchronize(tree->ctx->stream));
     return OIBVH_OK;
@@ -685,7 +727,7 @@ extern "C" int oibvh_tree_device_views(oibvh_tree* tree, const oibvh_aabb** dev_
     REQUIRE(tree != nullptr, "tree is NULL");
     if (dev_nodes) *dev_nodes = reinterpret_cast<const oibvh_aabb*>(tree->nodes);
     if (dev_sorted_faces) *dev_sorted_faces = tree->faces;
-    if (dev_positions) *dev_positions = tree->pos;
+    if (dev_positions) *dev_positions = reinterpret_cast<const float*>(tree->pos);
     return OIBVH_OK;
 }
 
@@ -788,30 +830,21 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     const uint32_t n_obj = (uint32_t)s->trees.size();
     uint32_t maxL = 0;
     for (auto* t : s->trees) maxL = std::max(maxL, t->L);
-    if (expand_levels == 0) expand_levels = (s->hint_front > (1u << 18)) ? 1u : 3u; // small fronts are latency-bound
-    expand_levels = std::min(expand_levels, 8u);
-    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 12u) : expand_levels;
+    if (expand_levels == 0) expand_levels = 3u;
+    expand_levels = std::min(expand_levels, 4u);  // one warp tests the 4^k descendant pairs of a node pair
+    // round 0 descends from the roots to the entry level (a hint: the pair set does not depend on it)
+    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 5u) : expand_levels;
     const uint32_t reached = std::min(k0, maxL);
-    const uint32_t rounds = 2 + (maxL - reached + expand_levels - 1) / expand_levels; // root round + ... + leaf round
+    const uint32_t rounds = 1 + (maxL - reached + expand_levels - 1) / expand_levels; // leaf pairs leave as candidates
     if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
 
     CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));
     {
+        // broad and narrow phase run inside one persistent kernel; the stage clock covers both
         StageScope scope(ctx, OIBVH_STAGE_BROAD);
-        CU(launch_seed(n_obj, s->front[0], s->front_cap, s->counters, st));
-        count_launch(ctx);
-        const uint32_t hint = std::max(s->hint_front, 1u << 14);
-        for (uint32_t r = 0; r < rounds; r++)
-        {
-            CU(launch_expand(s->d_objs, s->front[r & 1], s->front[(r + 1) & 1], s->front_cap, s->cand, s->cand_cap,
-                             s->counters, r, r == 0 ? k0 : expand_levels, s->rank, s->world, hint, st));
-            count_launch(ctx);
-        }
-    }
-    {
-        StageScope scope(ctx, OIBVH_STAGE_NARROW);
-        CU(launch_narrow(s->d_objs, s->cand, s->cand_cap, s->pairs, s->pair_cap, s->counters,
-                         std::max(s->hint_cand, 1u << 14), st));
+        CU(launch_collide(ctx->collide_grid, s->d_objs, n_obj, s->front[0], s->front[1], s->front_cap, s->cand,
+                          s->cand_cap, s->pairs, s->pair_cap, s->counters, rounds, k0, expand_levels, s->rank,
+                          s->world, st));
         count_launch(ctx);
     }
     CU(cudaMemcpyAsync(s->h_counters, s->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost, st));
@@ -869,6 +902,7 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         for (uint32_t r = 0; r <= scene->last_rounds; r++) max_front = std::max(max_front, h[CTR_FRONT0 + r]);
         scene->hint_front = max_front;
         scene->hint_cand = h[CTR_CANDIDATES];
+        if (h[CTR_OVERFLOW] & 8u) return fail(OIBVH_ERR_INTERNAL, "grid barrier timed out in the detection kernel");
         if (h[CTR_OVERFLOW] == 0)
         {
             if (n_pairs) *n_pairs = h[CTR_PAIRS];
@@ -921,6 +955,21 @@ extern "C" int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_
     int rc = oibvh_scene_get_counts(scene, n_pairs, nullptr);
     if (rc) return rc;
     *dev_pairs = reinterpret_cast<const oibvh_int_tri_pair*>(scene->pairs);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases,
+                                            uint32_t* n_phases)
+{
+    REQUIRE(scene && cycles && n_phases, "NULL argument");
+    int rc = oibvh_scene_get_counts(scene, nullptr, nullptr);
+    if (rc) return rc;
+    const uint32_t* h = scene->h_counters;
+    uint32_t stamps = h[CTR_TIME0 - 1];
+    if (stamps > (uint32_t)(CTR_WORDS - CTR_TIME0)) stamps = CTR_WORDS - CTR_TIME0;
+    const uint32_t n = stamps ? std::min(max_phases, stamps - 1) : 0;
+    for (uint32_t i = 0; i < n; i++) cycles[i] = h[CTR_TIME0 + i + 1] - h[CTR_TIME0 + i]; // wraps correctly
+    *n_phases = n;
     return OIBVH_OK;
 }
 

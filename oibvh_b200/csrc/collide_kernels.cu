@@ -15,7 +15,10 @@
 namespace oibvh
 {
 
-constexpr int kColThreads = 256;
+// One persistent cooperative kernel runs the whole detection: seeds -> every expansion round -> narrow phase, with a
+// grid-wide barrier between phases, so a detection costs one launch and the per-round latency is one barrier
+// (~1 us) instead of a kernel boundary. One CTA of 1024 threads per SM (148 arrivals per barrier).
+constexpr int kColThreads = 1024;
 constexpr int kColWarps = kColThreads / 32;
 
 __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, uint32_t i)
@@ -26,7 +29,7 @@ __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, ui
     ObjDesc d;
     d.nodes = reinterpret_cast<const float*>(((uint64_t)a.y << 32) | a.x);
     d.faces = reinterpret_cast<const uint32_t*>(((uint64_t)a.w << 32) | a.z);
-    d.pos = reinterpret_cast<const float*>(((uint64_t)b.y << 32) | b.x);
+    d.pos = reinterpret_cast<const float4*>(((uint64_t)b.y << 32) | b.x);
     d.T = b.z;
     d.L = b.w;
     return d;
@@ -37,8 +40,8 @@ __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, ui
 // Round 0 of the expansion turns them into the reference's entry-level seed rectangle (scene.cu:192-223)
 // and prunes object pairs whose root boxes do not overlap.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) seed_kernel(uint32_t n_obj, uint4* __restrict__ front, uint32_t front_cap,
-                                                   uint32_t* __restrict__ counters)
+__device__ void seed_phase(uint32_t n_obj, uint4* __restrict__ front, uint32_t front_cap,
+                           uint32_t* __restrict__ counters)
 {
     const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -60,121 +63,127 @@ __global__ void __launch_bounds__(256) seed_kernel(uint32_t n_obj, uint4* __rest
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// One round: test every node of the front, emit candidates (leaf, leaf) or the children rectangle
-// `levels` levels further down on each side (clamped to the leaf level and to the kept nodes of the level).
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kColThreads)
-    expand_kernel(const ObjDesc* __restrict__ objs, const uint4* __restrict__ in, uint4* __restrict__ out,
-                  uint32_t front_cap, uint4* __restrict__ cand, uint32_t cand_cap, uint32_t* __restrict__ counters,
-                  uint32_t round, uint32_t levels, uint32_t rank, uint32_t world)
+// Grid-wide barrier on a monotonically increasing arrival counter (zeroed with the counter block before the
+// launch). `generation` counts the barriers passed so far. The kernel is launched cooperatively, so every CTA is
+// resident and the spin terminates; a bounded spin turns a would-be hang into a reported failure.
+__device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters, uint32_t generation,
+                                                 const uint32_t* read_after)
 {
-    __shared__ uint32_t s_prefix[kColWarps][33];
-    __shared__ uint4 s_item[kColWarps][32]; // objA, objB, first child of A (packed), first child of B (packed)
-    __shared__ uint32_t s_nb[kColWarps][32];    // width of the children rectangle
-    __shared__ uint32_t s_first[kColWarps][32]; // shard striding: child c = first + m * step
-    __shared__ uint32_t s_step[kColWarps][32];
+    // returns *read_after as settled after the barrier, read ONCE per CTA and broadcast through shared memory
+    // (every warp of the chip polling the same word would serialise on one L2 slice)
+    __shared__ uint32_t s_value;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        atomicAdd(counters + CTR_BARRIER, 1u);
+        const uint32_t target = generation * gridDim.x;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(counters + CTR_BARRIER) < target)
+        {
+            __nanosleep(32);
+            if (++spins > (1u << 24))
+            {
+                atomicOr(counters + CTR_OVERFLOW, 8u);
+                break;
+            }
+        }
+        __threadfence();
+        s_value = __ldcg(read_after);
+    }
+    __syncthreads();
+    return s_value;
+}
 
+// ---------------------------------------------------------------------------------------------------
+// One round of BVTT expansion, warp-cooperative.
+//
+// A front entry is a node pair whose boxes are KNOWN to overlap (round 0: the untested root pairs). One warp takes
+// one pair, addresses the rectangle of descendants `levels` levels further down on each side (clamped to the leaf
+// level and to the nodes the level keeps), and its 32 lanes test the nA x nB descendant box pairs -- the 2^k + 2^k
+// boxes are two contiguous slices of the level arrays, so the loads are broadcast / L1 hits. Only overlapping
+// descendant pairs are emitted: to the next front, or to the candidate list when both sides reached the leaf level
+// (a candidate is by definition a leaf pair with overlapping boxes, src/cuda/collide.cu:155-162).
+// Emission is staged per warp in shared memory and flushed with ONE global atomic per ~200 records and
+// fully coalesced 16-byte stores; the grid is persistent (grid-stride over the front).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStageCap = 256; // records per warp staging buffer (4 KB)
+
+__device__ void expand_phase(uint4* s_stage, const ObjDesc* __restrict__ objs, const uint4* in, uint4* out,
+                             uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint32_t* counters, uint32_t round,
+                             uint32_t front_size, uint32_t levels, uint32_t rank, uint32_t world)
+{
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t n = min(counters[CTR_FRONT0 + round], front_cap);
+    // fronts are produced by other SMs inside this same launch: read them through L2 (ld.cg)
+    const uint32_t n = min(front_size, front_cap);
     uint32_t* next_count = counters + CTR_FRONT0 + round + 1;
     const uint32_t total_warps = gridDim.x * kColWarps;
+    uint4* stage = s_stage + warp * kStageCap;
+    uint32_t staged = 0;       // warp-uniform
+    bool staged_cand = false;  // warp-uniform: what the staged records are
 
-    for (uint32_t base = (blockIdx.x * kColWarps + warp) * 32; base < n; base += total_warps * 32)
+    auto flush = [&]() {
+        if (staged == 0) return;
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(staged_cand ? counters + CTR_CANDIDATES : next_count, staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint4* dst = staged_cand ? cand : out;
+        const uint32_t cap = staged_cand ? cand_cap : front_cap;
+        if (base + staged > cap && lane == 0) atomicOr(counters + CTR_OVERFLOW, staged_cand ? 2u : 1u);
+        for (uint32_t j = lane; j < staged; j += 32)
+            if (base + j < cap) dst[base + j] = stage[j];
+        __syncwarp();
+        staged = 0;
+    };
+
+    for (uint32_t p = blockIdx.x * kColWarps + warp; p < n; p += total_warps)
     {
-        const uint32_t i = base + lane;
-        const bool active = i < n;
-        uint32_t n_children = 0;
-        bool is_cand = false;
-        uint4 it = make_uint4(0, 0, 0, 0);
-        uint32_t child_a = 0, child_b = 0, nB = 1, first = 0, step = 1;
-        if (active)
+        const uint4 it = __ldcg(in + p); // same address in every lane: one broadcast load
+        const ObjDesc A = load_obj(objs, it.x), B = load_obj(objs, it.y);
+        const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
+        const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
+        const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
+        const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
+        if (round == 0)
         {
-            it = in[i];
-            const ObjDesc A = load_obj(objs, it.x), B = load_obj(objs, it.y);
-            const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
-            const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
-            const Box a = load_box(reinterpret_cast<const float2*>(A.nodes), level_offset(A.T, A.L, la) + pa);
-            const Box b = load_box(reinterpret_cast<const float2*>(B.nodes), level_offset(B.T, B.L, lb) + pb);
-            if (box_overlap(a, b))
+            // seeds are untested: prune object pairs whose root boxes are disjoint
+            const Box a = load_box(nodesA, level_offset(A.T, A.L, la) + pa);
+            const Box b = load_box(nodesB, level_offset(B.T, B.L, lb) + pb);
+            if (!box_overlap(a, b)) continue;
+        }
+        const uint32_t da = min(levels, A.L - la), db = min(levels, B.L - lb);
+        const uint32_t lca = la + da, lcb = lb + db;
+        const uint32_t fa = pa << da, fb = pb << db;
+        const uint32_t nA = min(1u << da, level_count(A.T, A.L, lca) - fa);
+        const uint32_t nB = min(1u << db, level_count(B.T, B.L, lcb) - fb);
+        const uint32_t baseA = level_offset(A.T, A.L, lca) + fa, baseB = level_offset(B.T, B.L, lcb) + fb;
+        const bool to_cand = (lca == A.L) && (lcb == B.L);
+        if (staged && to_cand != staged_cand) flush();
+        staged_cand = to_cand;
+        const uint32_t combos = nA * nB;
+        for (uint32_t c0 = 0; c0 < combos; c0 += 32)
+        {
+            const uint32_t c = c0 + lane;
+            bool hit = c < combos;
+            // round 0: the seed rectangle is dealt round-robin to the shards
+            if (world > 1 && round == 0 && hit) hit = ((p + c) % world) == rank;
+            const uint32_t ia = c / nB, ib = c - ia * nB;
+            if (hit) hit = box_overlap(load_box(nodesA, baseA + ia), load_box(nodesB, baseB + ib));
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const uint32_t cnt = __popc(mask);
+            if (staged + cnt > (uint32_t)kStageCap) flush();
+            if (hit)
             {
-                if (la == A.L && lb == B.L)
-                    is_cand = true;
-                else
-                {
-                    const uint32_t da = min(levels, A.L - la), db = min(levels, B.L - lb);
-                    const uint32_t fa = pa << da, fb = pb << db;
-                    const uint32_t nA = min(1u << da, level_count(A.T, A.L, la + da) - fa);
-                    nB = min(1u << db, level_count(B.T, B.L, lb + db) - fb);
-                    child_a = ((la + da) << kNodeLevelShift) | fa;
-                    child_b = ((lb + db) << kNodeLevelShift) | fb;
-                    const uint32_t all = nA * nB;
-                    if (world > 1 && round == 0)
-                    {
-                        // shard the seed rectangle round-robin; (i + c) % world == rank keeps child c
-                        first = (rank + world - (i % world)) % world;
-                        step = world;
-                        n_children = first < all ? (all - first + world - 1) / world : 0;
-                    }
-                    else
-                        n_children = all;
-                }
+                const uint32_t slot = staged + __popc(mask & lanemask_lt());
+                stage[slot] = to_cand ? make_uint4(it.x, it.y, fa + ia, fb + ib)
+                                      : make_uint4(it.x, it.y, (lca << kNodeLevelShift) | (fa + ia),
+                                                   (lcb << kNodeLevelShift) | (fb + ib));
             }
+            staged += cnt;
         }
-
-        // ---- candidates: one atomic per warp ----
-        const uint32_t cmask = __ballot_sync(0xffffffffu, is_cand);
-        if (cmask)
-        {
-            uint32_t cbase = 0;
-            if (lane == 0) cbase = atomicAdd(counters + CTR_CANDIDATES, (uint32_t)__popc(cmask));
-            cbase = __shfl_sync(0xffffffffu, cbase, 0);
-            if (is_cand)
-            {
-                const uint32_t dst = cbase + __popc(cmask & lanemask_lt());
-                if (dst < cand_cap)
-                    cand[dst] = make_uint4(it.x, it.y, it.z & kNodePosMask, it.w & kNodePosMask);
-                else
-                    atomicOr(counters + CTR_OVERFLOW, 2u);
-            }
-        }
-
-        // ---- children: warp prefix sum, one atomic, cooperative coalesced emission ----
-        uint32_t inc = n_children;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        if (total == 0) continue;
-        s_prefix[warp][lane] = inc - n_children;
-        if (lane == 31) s_prefix[warp][32] = total;
-        s_item[warp][lane] = make_uint4(it.x, it.y, child_a, child_b);
-        s_nb[warp][lane] = nB;
-        s_first[warp][lane] = first;
-        s_step[warp][lane] = step;
-        uint32_t obase = 0;
-        if (lane == 0) obase = atomicAdd(next_count, total);
-        obase = __shfl_sync(0xffffffffu, obase, 0);
-        __syncwarp();
-        if (obase + total > front_cap && lane == 0) atomicOr(counters + CTR_OVERFLOW, 1u);
-        for (uint32_t j = lane; j < total; j += 32)
-        {
-            // owner lane: largest s with prefix[s] <= j
-            uint32_t s = 0;
-#pragma unroll
-            for (int bit = 16; bit > 0; bit >>= 1)
-                if (s_prefix[warp][s + bit] <= j) s += bit;
-            const uint32_t m = j - s_prefix[warp][s];
-            const uint32_t nb = s_nb[warp][s];
-            const uint32_t c = s_first[warp][s] + m * s_step[warp][s];
-            const uint4 src = s_item[warp][s];
-            if (obase + j < front_cap) out[obase + j] = make_uint4(src.x, src.y, src.z + c / nb, src.w + c % nb);
-        }
-        __syncwarp();
     }
+    flush();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -253,18 +262,17 @@ __device__ bool triangles_intersect(const V3& P1, const V3& P2, const V3& P3, co
     return true;
 }
 
-__device__ __forceinline__ V3 load_v3(const float* __restrict__ pos, uint32_t v)
+__device__ __forceinline__ V3 load_v3(const float4* __restrict__ pos, uint32_t v)
 {
-    const float* p = pos + 3ull * v;
-    return V3{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    const float4 p = __ldg(pos + v);
+    return V3{p.x, p.y, p.z};
 }
 
-__global__ void __launch_bounds__(kColThreads)
-    narrow_kernel(const ObjDesc* __restrict__ objs, const uint4* __restrict__ cand, uint32_t cand_cap,
-                  uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ counters)
+__device__ void narrow_phase(const ObjDesc* __restrict__ objs, const uint4* cand, uint32_t cand_cap,
+                             uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* counters, uint32_t n_cand)
 {
     const uint32_t lane = lane_id();
-    const uint32_t n = min(counters[CTR_CANDIDATES], cand_cap);
+    const uint32_t n = min(n_cand, cand_cap);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride)
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(kColThreads)
         uint4 c = make_uint4(0, 0, 0, 0);
         if (i < n)
         {
-            c = cand[i];
+            c = __ldcg(cand + i);
             const ObjDesc A = load_obj(objs, c.x), B = load_obj(objs, c.y);
             const uint32_t* fa = A.faces + 3ull * c.z;
             const uint32_t* fb = B.faces + 3ull * c.w;
@@ -300,39 +308,67 @@ __global__ void __launch_bounds__(kColThreads)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Launchers
+// The persistent detection kernel
 // ---------------------------------------------------------------------------------------------------
-static inline uint32_t persistent_grid(uint64_t work_items, uint32_t per_block, uint32_t blocks_per_sm)
+__global__ void __launch_bounds__(kColThreads, 1)
+    collide_kernel(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* front0, uint4* front1, uint32_t front_cap,
+                   uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap, uint32_t* counters,
+                   uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world)
 {
-    uint64_t b = (work_items + per_block - 1) / per_block;
-    const uint64_t cap = (uint64_t)kNumSMsB200 * blocks_per_sm;
-    if (b > cap) b = cap;
-    if (b == 0) b = 1;
-    return (uint32_t)b;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* s_stage = reinterpret_cast<uint4*>(smem_raw); // kColWarps x kStageCap records
+    uint32_t gen = 0;
+    auto stamp = [&](uint32_t i) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && i < CTR_WORDS - CTR_TIME0) counters[CTR_TIME0 + i] = (uint32_t)clock64();
+    };
+    stamp(0);
+    seed_phase(n_obj, front0, front_cap, counters);
+    uint32_t front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0);
+    stamp(gen);
+    for (uint32_t r = 0; r < rounds && front_size != 0; r++) // front_size is uniform over the grid
+    {
+        uint4* in = (r & 1) ? front1 : front0;
+        uint4* out = (r & 1) ? front0 : front1;
+        expand_phase(s_stage, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size,
+                     r == 0 ? levels0 : levels, rank, world);
+        front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0 + r + 1);
+        stamp(gen);
+    }
+    const uint32_t n_cand = grid_barrier(counters, ++gen, counters + CTR_CANDIDATES);
+    stamp(gen);
+    narrow_phase(objs, cand, cand_cap, pairs, pair_cap, counters, n_cand);
+    __syncthreads();
+    stamp(gen + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = gen + 2; // number of stamps
 }
 
-cudaError_t launch_seed(uint32_t n_obj, uint4* front, uint32_t front_cap, uint32_t* counters, cudaStream_t s)
+constexpr size_t kColSmemBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 128 KB
+
+cudaError_t collide_configure(int* grid_blocks)
 {
-    const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
-    seed_kernel<<<persistent_grid(n_pairs, 256, 8), 256, 0, s>>>(n_obj, front, front_cap, counters);
-    return cudaGetLastError();
+    cudaError_t e = cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0, dev = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collide_kernel, kColThreads, kColSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *grid_blocks = sms; // one CTA per SM: the fewest barrier arrivals
+    return cudaSuccess;
 }
 
-cudaError_t launch_expand(const ObjDesc* objs, const uint4* in, uint4* out, uint32_t front_cap, uint4* cand,
-                          uint32_t cand_cap, uint32_t* counters, uint32_t round, uint32_t levels, uint32_t rank,
-                          uint32_t world, uint32_t grid_hint, cudaStream_t s)
+cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
+                           uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
+                           uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
+                           uint32_t world, cudaStream_t s)
 {
-    expand_kernel<<<persistent_grid(grid_hint, kColThreads, 8), kColThreads, 0, s>>>(
-        objs, in, out, front_cap, cand, cand_cap, counters, round, levels, rank, world);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_narrow(const ObjDesc* objs, const uint4* cand, uint32_t cand_cap, uint4* pairs,
-                          uint32_t pair_cap, uint32_t* counters, uint32_t grid_hint, cudaStream_t s)
-{
-    narrow_kernel<<<persistent_grid(grid_hint, kColThreads, 8), kColThreads, 0, s>>>(objs, cand, cand_cap, pairs,
-                                                                                      pair_cap, counters);
-    return cudaGetLastError();
+    void* args[] = {&objs, &n_obj, &front0, &front1, &front_cap, &cand, &cand_cap, &pairs, &pair_cap,
+                    &counters, &rounds, &levels0, &levels, &rank, &world};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(collide_kernel), dim3(grid_blocks),
+                                       dim3(kColThreads), args, kColSmemBytes, s);
 }
 
 } // namespace oibvh

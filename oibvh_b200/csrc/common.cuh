@@ -155,4 +155,57 @@ __device__ __forceinline__ void store_box(float2* __restrict__ nodes, uint32_t i
     p[2] = make_float2(o.hy, o.hz);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block / grid collectives
+// ------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_totals /* THREADS/32 */)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+    }
+    if (lane == 31) warp_totals[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++)
+        if ((uint32_t)w < warp) base += warp_totals[w];
+    __syncthreads();
+    return base + inc - v;
+}
+
+
+// Grid-wide barrier for cooperatively launched kernels: monotonically increasing arrival counter (zeroed before the
+// launch), `generation` = number of barriers including this one. One thread per CTA fences, arrives and spins;
+// the fence is cumulative over the CTA barrier, so every thread's earlier global writes are visible to every
+// thread of the grid afterwards (readers must bypass L1: __ldcg / ld.relaxed.gpu). A bounded spin turns a would-be
+// hang into a failure flag.
+__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation, uint32_t* fail_flag)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const uint32_t target = generation * gridDim.x;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(counter) < target)
+        {
+            __nanosleep(32);
+            if (++spins > (1u << 24))
+            {
+                atomicOr(fail_flag, 1u);
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 } // namespace oibvh

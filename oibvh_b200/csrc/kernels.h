@@ -22,16 +22,27 @@ constexpr int kSortItemsPerThread = 16;
 constexpr int kSortTile = (1 << kRadixBits) * kSortItemsPerThread;
 
 // ---- build / refit ----
-cudaError_t launch_morton_hist(const uint32_t* faces, const float* pos, uint32_t T, const MeshAabb& mesh,
+// boundary layout conversion: packed xyz <-> float4 (w = 1), packed index triples -> uint4 (w = 0)
+cudaError_t launch_pack_positions(const float* xyz, float4* pos4, uint32_t V, cudaStream_t s);
+cudaError_t launch_unpack_positions(const float4* pos4, float* xyz, uint32_t V, cudaStream_t s);
+cudaError_t launch_pack_faces(const uint32_t* f3, uint4* faces4, uint32_t T, cudaStream_t s);
+cudaError_t launch_morton_hist(const uint4* faces4, const float4* pos4, uint32_t T, const MeshAabb& mesh,
                                uint32_t* keys, uint32_t* hist, cudaStream_t s);
 uint32_t onesweep_tiles(uint32_t T);
 cudaError_t launch_onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                                  uint32_t* vals_out, uint32_t T, int pass, const uint32_t* hist, uint32_t* status,
                                  uint32_t* ticket, cudaStream_t s);
+// cooperative all-passes-in-one-launch sort for single-wave sizes (sort_coop.cu); result in (keys_a, vals_a).
+// ctl: coop_sort_ctl_words() words whose first 64 are zeroed before every launch.
+cudaError_t coop_sort_configure();
+uint32_t coop_sort_capacity(); // largest T the cooperative kernel takes on this device
+size_t coop_sort_ctl_words();
+cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
+                             uint32_t* ctl, cudaStream_t s);
 cudaError_t tree_emit_configure();
-cudaError_t launch_tree_emit(bool build, const uint32_t* faces_in, const uint32_t* perm, uint32_t* faces_sorted,
-                             const float* pos, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s);
-cudaError_t launch_transform(float* pos, uint32_t V, const Mat4& M, cudaStream_t s);
+cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
+                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s);
+cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream_t s);
 
 // ---- collision ----
 // one entry of the device object table (Scene::m_aabbOffsets/m_primOffsets/m_vertexOffsets/m_primCounts of the
@@ -40,7 +51,7 @@ struct ObjDesc
 {
     const float* nodes;    // N x 6 floats, real-index order
     const uint32_t* faces; // T x 3, Morton order
-    const float* pos;      // V x 3
+    const float4* pos;     // V x (x, y, z, 1)
     uint32_t T;
     uint32_t L; // leaf level = ceil(log2 T)
 };
@@ -54,20 +65,21 @@ enum
 {
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
-    CTR_OVERFLOW = 2, // bit 0: front, bit 1: candidates, bit 2: pairs
+    CTR_OVERFLOW = 2, // bit 0: front, bit 1: candidates, bit 2: pairs, bit 3: grid barrier timed out
+    CTR_BARRIER = 3,  // arrival counter of the grid barrier
     CTR_FRONT0 = 8,   // CTR_FRONT0 + r = size of the front consumed by round r
     CTR_MAX_ROUNDS = 48,
-    CTR_WORDS = CTR_FRONT0 + CTR_MAX_ROUNDS + 8
+    CTR_TIME0 = 64,   // CTR_TIME0 + i = SM cycle counter (low 32 bits) of CTA 0 at phase boundary i
+    CTR_WORDS = 128
 };
 
-// front[p] = (i, j, root, root) for the p-th object pair i < j; counters[CTR_FRONT0] = number of pairs
-cudaError_t launch_seed(uint32_t n_obj, uint4* front, uint32_t front_cap, uint32_t* counters, cudaStream_t s);
-// round `round`: consumes counters[CTR_FRONT0 + round] nodes of `in`, descends `levels` levels per side.
-// rank/world shard the children of round 0. grid_hint = expected front size (sizes the persistent grid).
-cudaError_t launch_expand(const ObjDesc* objs, const uint4* in, uint4* out, uint32_t front_cap, uint4* cand,
-                          uint32_t cand_cap, uint32_t* counters, uint32_t round, uint32_t levels, uint32_t rank,
-                          uint32_t world, uint32_t grid_hint, cudaStream_t s);
-cudaError_t launch_narrow(const ObjDesc* objs, const uint4* cand, uint32_t cand_cap, uint4* pairs,
-                          uint32_t pair_cap, uint32_t* counters, uint32_t grid_hint, cudaStream_t s);
+// Whole detection in one cooperative launch: seeds (one root pair per object pair i<j) -> `rounds` expansion
+// rounds (round 0 descends levels0 levels, the others `levels`; rank/world shard the children of round 0) ->
+// narrow phase. counters must be zeroed before the launch. grid_blocks comes from collide_configure().
+cudaError_t collide_configure(int* grid_blocks);
+cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
+                           uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
+                           uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
+                           uint32_t world, cudaStream_t s);
 
 } // namespace oibvh

@@ -1,5 +1,7 @@
 // Build / refit kernels of the ostensibly-implicit BVH for sm_100a.
 //
+//   pack_* / unpack_*    boundary layout conversion: packed xyz / packed index triples <-> 16-byte records, so that
+//                        every gather on the hot path is ONE 128-bit load (one L2 sector) instead of three
 //   morton_hist_kernel   faces + positions -> 30-bit Morton keys (+ all radix-digit histograms in the same pass)
 //   onesweep_pass_kernel one stable LSD radix pass (key, face id) with decoupled look-back (single sweep per digit)
 //   tree_emit_kernel     leaf AABBs + the whole bottom-up AABB reduction of a 1024-leaf subtree per CTA in
@@ -14,6 +16,32 @@
 
 namespace oibvh
 {
+
+// =================================================================================================
+// Layout conversion at the boundary
+// =================================================================================================
+__global__ void __launch_bounds__(256) pack_pos_kernel(const float* __restrict__ xyz, float4* __restrict__ out, uint32_t V)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float* p = xyz + 3ull * i;
+    out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+__global__ void __launch_bounds__(256) unpack_pos_kernel(const float4* __restrict__ in, float* __restrict__ xyz, uint32_t V)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float4 v = in[i];
+    float* p = xyz + 3ull * i;
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+__global__ void __launch_bounds__(256) pack_faces_kernel(const uint32_t* __restrict__ f3, uint4* __restrict__ out, uint32_t T)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const uint32_t* f = f3 + 3ull * i;
+    out[i] = make_uint4(f[0], f[1], f[2], 0u);
+}
 
 // =================================================================================================
 // Morton keys
@@ -40,25 +68,9 @@ __device__ __forceinline__ uint32_t quantise10(float q)
     return (b != b) ? 0u : __float2uint_rz(b);
 }
 
-struct Vec3
-{
-    float x, y, z;
-};
-
-__device__ __forceinline__ Vec3 load_pos(const float* __restrict__ pos, uint32_t v)
-{
-    const float* p = pos + 3ull * v;
-    Vec3 r;
-    r.x = __ldg(p);
-    r.y = __ldg(p + 1);
-    r.z = __ldg(p + 2);
-    return r;
-}
-
 // glm::min(glm::min(v0, v1), v2) / glm::max(glm::max(v0, v1), v2)   (src/cuda/oibvh.cu:33-39)
-__device__ __forceinline__ Box face_box(const float* __restrict__ pos, uint32_t i0, uint32_t i1, uint32_t i2)
+__device__ __forceinline__ Box box_of(const float4& a, const float4& b, const float4& c)
 {
-    const Vec3 a = load_pos(pos, i0), b = load_pos(pos, i1), c = load_pos(pos, i2);
     Box o;
     o.lx = gmin(gmin(a.x, b.x), c.x);
     o.ly = gmin(gmin(a.y, b.y), c.y);
@@ -82,75 +94,64 @@ __device__ __forceinline__ uint32_t morton_of_box(const Box& b, const MeshAabb& 
     return (spread3(quantise10(qx)) << 2) | (spread3(quantise10(qy)) << 1) | spread3(quantise10(qz));
 }
 
-// warp-aggregated shared-memory histogram update: one atomic per distinct digit per warp
-__device__ __forceinline__ void hist_add(uint32_t* h, uint32_t digit, bool valid)
-{
-    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0xffffffffu);
-    if (valid && lane_id() == (uint32_t)(__ffs(peers) - 1)) atomicAdd(h + digit, (uint32_t)__popc(peers));
-}
+constexpr int kMortonFacesPerThread = 4;
 
-template <int RADIX_BITS, int PASSES>
-__global__ void __launch_bounds__(256) morton_hist_kernel(const uint32_t* __restrict__ faces,
-                                                          const float* __restrict__ pos, uint32_t T, MeshAabb mesh,
+template <int RADIX_BITS, int PASSES, bool HIST>
+__global__ void __launch_bounds__(256) morton_hist_kernel(const uint4* __restrict__ faces4,
+                                                          const float4* __restrict__ pos4, uint32_t T, MeshAabb mesh,
                                                           uint32_t* __restrict__ keys, uint32_t* __restrict__ hist)
 {
     constexpr int RADIX = 1 << RADIX_BITS;
-    __shared__ uint32_t sh[PASSES * RADIX];
-    for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-
-    const uint32_t groups = (T + 3) / 4; // 4 faces = 48 B = three 128-bit loads
-    const uint4* f4 = reinterpret_cast<const uint4*>(faces);
-    // whole warps iterate together so the match in hist_add always sees 32 lanes
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounded = (groups + 31u) & ~31u;
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += stride)
+    __shared__ uint32_t sh[HIST ? PASSES * RADIX : 1];
+    if (HIST)
     {
-        uint32_t idx[12];
-        const uint32_t f0 = g * 4;
-        const bool full = g < groups && f0 + 4 <= T;
-        if (full)
-        {
-            const uint4 a = ldg_stream_u4(f4 + 3ull * g), b = ldg_stream_u4(f4 + 3ull * g + 1),
-                        c = ldg_stream_u4(f4 + 3ull * g + 2);
-            idx[0] = a.x; idx[1] = a.y; idx[2] = a.z; idx[3] = a.w;
-            idx[4] = b.x; idx[5] = b.y; idx[6] = b.z; idx[7] = b.w;
-            idx[8] = c.x; idx[9] = c.y; idx[10] = c.z; idx[11] = c.w;
-        }
-        else
-        {
+        for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
+
+    // block-strided tiles of 256 x 4 faces; lane-consecutive faces are memory-consecutive (one 128-bit load each)
+    const uint32_t tile = 256 * kMortonFacesPerThread;
+    for (uint64_t base = (uint64_t)blockIdx.x * tile; base < T; base += (uint64_t)gridDim.x * tile)
+    {
+        uint4 f[kMortonFacesPerThread];
+        bool valid[kMortonFacesPerThread];
 #pragma unroll
-            for (int k = 0; k < 12; k++)
+        for (int k = 0; k < kMortonFacesPerThread; k++)
+        {
+            const uint64_t i = base + k * 256 + threadIdx.x;
+            valid[k] = i < T;
+            f[k] = valid[k] ? ldg_stream_u4(faces4 + i) : make_uint4(0, 0, 0, 0);
+        }
+        float4 v[kMortonFacesPerThread][3];
+#pragma unroll
+        for (int k = 0; k < kMortonFacesPerThread; k++)
+        {
+            v[k][0] = __ldg(pos4 + f[k].x);
+            v[k][1] = __ldg(pos4 + f[k].y);
+            v[k][2] = __ldg(pos4 + f[k].z);
+        }
+#pragma unroll
+        for (int k = 0; k < kMortonFacesPerThread; k++)
+        {
+            if (!valid[k]) continue;
+            const uint32_t key = morton_of_box(box_of(v[k][0], v[k][1], v[k][2]), mesh);
+            keys[base + k * 256 + threadIdx.x] = key;
+            if (HIST)
             {
-                const uint64_t e = 12ull * g + k;
-                idx[k] = (g < groups && e < 3ull * T) ? faces[e] : 0u;
+#pragma unroll
+                for (int p = 0; p < PASSES; p++)
+                    atomicAdd(sh + p * RADIX + ((key >> (p * RADIX_BITS)) & (RADIX - 1)), 1u);
             }
         }
-        uint32_t key[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-        {
-            const bool valid = g < groups && f0 + k < T;
-            key[k] = 0;
-            if (valid) key[k] = morton_of_box(face_box(pos, idx[3 * k], idx[3 * k + 1], idx[3 * k + 2]), mesh);
-#pragma unroll
-            for (int p = 0; p < PASSES; p++)
-                hist_add(sh + p * RADIX, (key[k] >> (p * RADIX_BITS)) & (RADIX - 1), valid);
-        }
-        if (full)
-            *reinterpret_cast<uint4*>(keys + f0) = make_uint4(key[0], key[1], key[2], key[3]);
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (g < groups && f0 + k < T) keys[f0 + k] = key[k];
-        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x)
+    if (HIST)
     {
-        const uint32_t c = sh[i];
-        if (c) atomicAdd(hist + i, c);
+        __syncthreads();
+        for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x)
+        {
+            const uint32_t c = sh[i];
+            if (c) atomicAdd(hist + i, c);
+        }
     }
 }
 
@@ -162,27 +163,19 @@ constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kCountMask = ~kFlagMask;
+constexpr int kLookbackBatch = 8; // predecessor status words fetched per round trip
 
-template <int THREADS>
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_totals /* THREADS/32 */)
-{
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (uint32_t)o) inc += n;
-    }
-    if (lane == 31) warp_totals[warp] = inc;
-    __syncthreads();
-    uint32_t base = 0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; w++)
-        if ((uint32_t)w < warp) base += warp_totals[w];
-    __syncthreads();
-    return base + inc - v;
-}
+#ifdef OIBVH_PROFILE
+__device__ unsigned long long g_sort_prof[4][2][8]; // [pass][first/last tile][stamp]
+#define SORT_STAMP(k)                                                                                              \
+    do                                                                                                             \
+    {                                                                                                              \
+        if (threadIdx.x == 0 && (tile == 0 || tile == gridDim.x - 1))                                              \
+            g_sort_prof[shift / RADIX_BITS][tile == 0 ? 0 : 1][k] = clock64();                                     \
+    } while (0)
+#else
+#define SORT_STAMP(k)
+#endif
 
 template <int RADIX_BITS, int IPT>
 __global__ void __launch_bounds__(1 << RADIX_BITS)
@@ -198,6 +191,9 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
 
     __shared__ uint32_t s_hist[WARPS][RADIX];
     __shared__ uint32_t s_keys[TILE];
+    // per-warp peer masks of the ranking phase live in the (not yet used) key staging area
+    static_assert(WARPS * RADIX <= TILE, "peer masks must fit in the key staging area");
+    uint32_t(*s_mask)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_keys);
     __shared__ uint32_t s_vals[TILE];
     __shared__ uint32_t s_digit_base[RADIX];
     __shared__ uint32_t s_global_base[RADIX];
@@ -207,14 +203,19 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u); // tiles are claimed in launch order: predecessors are resident
 #pragma unroll
-    for (int w = 0; w < WARPS; w++) s_hist[w][tid] = 0;
+    for (int w = 0; w < WARPS; w++)
+    {
+        s_hist[w][tid] = 0;
+        s_mask[w][tid] = 0;
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * TILE;
     const uint32_t tile_valid = min((uint32_t)TILE, T - tile_base);
+    SORT_STAMP(0);
 
     // ---- load (warp-striped: lane-consecutive keys are memory-consecutive) + stable in-warp ranking ----
-    uint32_t key[IPT];
+    uint32_t key[IPT], val[IPT];
     uint16_t rank[IPT];
     const uint32_t warp_base = tile_base + warp * (32 * IPT);
 #pragma unroll
@@ -223,27 +224,46 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
         const uint32_t i = warp_base + j * 32 + lane;
         key[j] = (i < T) ? ldg_stream_u32(keys_in + i) : 0xffffffffu;
     }
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+    {
+        const uint32_t i = warp_base + j * 32 + lane;
+        val[j] = (vals_in && i < T) ? ldg_stream_u32(vals_in + i) : i; // first pass: the value is the face id
+    }
+    SORT_STAMP(1);
+    // Stable in-warp ranking. Peer groups (lanes holding the same digit) are found with one shared-memory atomicOr
+    // per lane into a per-warp, per-digit lane mask: constant cost, unlike match.any whose latency grows with the
+    // number of distinct digits in the warp (32 for the high-entropy low digits of a Morton key).
     uint32_t* my_hist = s_hist[warp];
+    uint32_t* my_mask = s_mask[warp];
+    const uint32_t lane_bit = 1u << lane;
 #pragma unroll
     for (int j = 0; j < IPT; j++)
     {
         const uint32_t i = warp_base + j * 32 + lane;
         const bool valid = i < T;
         const uint32_t d = (key[j] >> shift) & MASK;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (uint32_t)RADIX);
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader)
+        if (valid) atomicOr(my_mask + d, lane_bit);
+        __syncwarp();
+        uint32_t peers = 0, before = 0;
+        if (valid)
         {
-            old = my_hist[d];
-            my_hist[d] = old + __popc(peers);
+            peers = my_mask[d];
+            before = my_hist[d];
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[j] = (uint16_t)(old + __popc(peers & lanemask_lt()));
+        const uint32_t lower = __popc(peers & lanemask_lt());
+        rank[j] = (uint16_t)(before + lower);
+        __syncwarp();
+        if (valid && lower == 0) // lowest lane of the group closes it
+        {
+            my_hist[d] = before + __popc(peers);
+            my_mask[d] = 0;
+        }
         __syncwarp();
     }
     __syncthreads();
 
+    SORT_STAMP(2);
     // ---- per-digit: warp-exclusive offsets, tile count, tile-local digit base, global base via look-back ----
     {
         const uint32_t d = tid;
@@ -258,26 +278,44 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
         const uint32_t tile_count = run;
         uint32_t* my_status = status + (size_t)tile * RADIX + d;
         // publish the aggregate first so successors can make progress while we scan
-        if (tile == 0)
-            st_relaxed_gpu(my_status, kFlagPrefix | tile_count);
-        else
-            st_relaxed_gpu(my_status, kFlagAggregate | tile_count);
+        st_relaxed_gpu(my_status, (tile == 0 ? kFlagPrefix : kFlagAggregate) | tile_count);
 
         const uint32_t bin_start = block_exclusive_scan<THREADS>(hist[d], s_scan);
         const uint32_t digit_base = block_exclusive_scan<THREADS>(tile_count, s_scan);
 
+        SORT_STAMP(3);
         uint32_t exclusive = 0;
         if (tile != 0)
         {
+            // decoupled look-back, kLookbackBatch predecessors per round trip: consume them in order, stop at the
+            // first inclusive prefix, re-issue from the first unpublished one. (Efficient in the streaming regime,
+            // tiles >> resident CTAs, where the predecessor is usually complete; single-wave sizes use the
+            // cooperative kernel below instead.)
             int t = (int)tile - 1;
-            while (true)
+            bool done = false;
+            while (!done)
             {
-                const uint32_t s = ld_relaxed_gpu(status + (size_t)t * RADIX + d);
-                const uint32_t f = s & kFlagMask;
-                if (f == 0) continue; // predecessor not published yet (it is resident: ticket order)
-                exclusive += s & kCountMask;
-                if (f == kFlagPrefix) break;
-                t--;
+                uint32_t w[kLookbackBatch];
+#pragma unroll
+                for (int b = 0; b < kLookbackBatch; b++)
+                    w[b] = (t - b >= 0) ? ld_relaxed_gpu(status + (size_t)(t - b) * RADIX + d) : kFlagPrefix;
+                bool stop = false;
+#pragma unroll
+                for (int b = 0; b < kLookbackBatch; b++)
+                {
+                    const uint32_t f = w[b] & kFlagMask;
+                    if (!stop && !done)
+                    {
+                        if (f == 0)
+                            stop = true; // not published yet (it is resident: ticket order) -> retry from here
+                        else
+                        {
+                            exclusive += w[b] & kCountMask;
+                            t--;
+                            if (f == kFlagPrefix) done = true;
+                        }
+                    }
+                }
             }
             st_relaxed_gpu(my_status, kFlagPrefix | (exclusive + tile_count));
         }
@@ -286,6 +324,7 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
     }
     __syncthreads();
 
+    SORT_STAMP(4);
     // ---- reorder inside the tile through shared memory, then write digit runs coalesced ----
     uint16_t slot[IPT];
 #pragma unroll
@@ -300,9 +339,10 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
     for (int j = 0; j < IPT; j++)
     {
         const uint32_t i = warp_base + j * 32 + lane;
-        if (i < T) s_vals[slot[j]] = vals_in ? ldg_stream_u32(vals_in + i) : i;
+        if (i < T) s_vals[slot[j]] = val[j];
     }
     __syncthreads();
+    SORT_STAMP(5);
 #pragma unroll
     for (int k = 0; k < IPT; k++)
     {
@@ -315,19 +355,29 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
             vals_out[dst] = s_vals[s];
         }
     }
+    SORT_STAMP(6);
 }
 
 // =================================================================================================
-// Leaf boxes + bottom-up reduction, one CHUNK-leaf subtree per CTA.
+// Leaf boxes + bottom-up reduction, one CHUNK-leaf subtree per CTA, one 128-leaf subtree per warp.
+//
+// thread: 4 consecutive leaves -> heights 0..2 in registers
+// warp:   heights 3..7 by shuffles; the warp's nodes of every height are a contiguous slice of that level in
+//         global memory, so they are staged in a 3 KB per-warp buffer and copied out coalesced
+// CTA:    heights 8..10 from the 8 warp roots
+// grid:   the last CTA to retire reduces the chunk roots to the tree root (finish_top)
 // =================================================================================================
 constexpr int kEmitThreads = 256;
+constexpr int kEmitWarps = kEmitThreads / 32;
 constexpr int kLeavesPerThread = 4;
+constexpr int kWarpLeaves = 32 * kLeavesPerThread;      // 128
 constexpr int kChunk = kEmitThreads * kLeavesPerThread; // 1024 leaves
 constexpr int kChunkLevels = 10;                        // log2(kChunk)
-// staging: nodes of local height h (0 = leaves) occupy slots [sm_off(h), sm_off(h) + (kChunk >> h))
-__device__ __forceinline__ constexpr int sm_off(int h) { return 2 * kChunk - (2 * kChunk >> h); }
-constexpr int kStageNodes = 2 * kChunk - 1;
-constexpr size_t kEmitSmemBytes = (size_t)kStageNodes * 24 + 16;
+constexpr int kWarpLevels = 7;                          // log2(kWarpLeaves)
+constexpr int kTopSmemNodes = 512;                      // finish_top switches to shared memory at this width
+
+// slot of the first height-h node inside a warp's staging area (h = 1..7): 0, 64, 96, 112, 120, 124, 126
+__device__ __forceinline__ constexpr int woff(int h) { return kWarpLeaves - (2 * kWarpLeaves >> h); }
 
 __device__ __forceinline__ void stage_box(float2* sm, int slot, const Box& b)
 {
@@ -363,13 +413,29 @@ __device__ __forceinline__ Box load_box_cg(const float2* nodes, uint32_t idx)
     return o;
 }
 
+// warp-cooperative copy of n8 8-byte words from shared to global memory; 16-byte stores wherever dst allows
+__device__ __forceinline__ void warp_copy_out(float2* __restrict__ dst, const float2* src, uint32_t n8, uint32_t lane)
+{
+    uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1u); // 1 if dst is only 8-byte aligned
+    if (head > n8) head = n8;
+    if (lane == 0 && head) dst[0] = src[0];
+    const uint32_t body = (n8 - head) >> 1; // 16-byte words
+    float4* d4 = reinterpret_cast<float4*>(dst + head);
+    for (uint32_t i = lane; i < body; i += 32)
+    {
+        const float2 a = src[head + 2 * i], b = src[head + 2 * i + 1];
+        d4[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+    if (lane == 0 && ((n8 - head) & 1u)) dst[n8 - 1] = src[n8 - 1];
+}
+
 // Levels [0, top_level) of the tree, given that level `top_level` is complete in global memory.
-// Run by one CTA (the last one to finish its chunk). Uses the staging buffer as two ping-pong arrays.
+// Run by one CTA (the last one to finish its chunk). `sm` holds at least 1.5 * kTopSmemNodes nodes.
 __device__ void finish_top(float2* __restrict__ nodes, float2* sm, uint32_t T, uint32_t L, uint32_t top_level)
 {
     uint32_t l = top_level;
     // wide levels: straight through L2
-    while (l > 0 && level_count(T, L, l) > (uint32_t)kChunk)
+    while (l > 0 && level_count(T, L, l) > (uint32_t)kTopSmemNodes)
     {
         const uint32_t cnt_c = level_count(T, L, l), cnt_p = level_count(T, L, l - 1);
         const uint32_t off_c = level_offset(T, L, l), off_p = level_offset(T, L, l - 1);
@@ -386,7 +452,7 @@ __device__ void finish_top(float2* __restrict__ nodes, float2* sm, uint32_t T, u
     if (l == 0) return;
     // narrow levels: shared memory
     float2* cur = sm;
-    float2* nxt = sm + 3 * kChunk;
+    float2* nxt = sm + 3 * kTopSmemNodes;
     uint32_t cnt_c = level_count(T, L, l);
     {
         const float2* src = nodes + 3ull * level_offset(T, L, l);
@@ -411,21 +477,29 @@ __device__ void finish_top(float2* __restrict__ nodes, float2* sm, uint32_t T, u
     }
 }
 
+// shared memory: per-warp staging, 8 x 128 nodes x 24 B = 24 KB, reused by finish_top (512 + 256 nodes)
+constexpr int kEmitStageNodes = kEmitWarps * kWarpLeaves; // 1024
+constexpr size_t kEmitSmemBytes = (size_t)kEmitStageNodes * 24;
+static_assert(kTopSmemNodes + kTopSmemNodes / 2 <= kEmitStageNodes, "finish_top staging must fit");
+
 template <bool BUILD>
-__global__ void __launch_bounds__(kEmitThreads)
-    tree_emit_kernel(const uint32_t* __restrict__ faces_in,   // BUILD: input-order faces ; else: sorted faces
+__global__ void __launch_bounds__(kEmitThreads, 5)
+    tree_emit_kernel(const uint4* __restrict__ faces_in4,     // BUILD: input-order faces (16-byte records)
                      const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
-                     uint32_t* __restrict__ faces_sorted,     // BUILD: output
-                     const float* __restrict__ pos, float2* __restrict__ nodes, uint32_t T, uint32_t L,
+                     uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
+                     const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
                      uint32_t* done_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
+    __shared__ float2 s_top[3 * 16]; // heights 7..10 of the chunk: 8 + 4 + 2 + 1 nodes
     __shared__ bool s_last;
 
-    const uint32_t tid = threadIdx.x, lane = lane_id();
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint32_t chunk = blockIdx.x;
-    const uint32_t leaf0 = chunk * kChunk + tid * kLeavesPerThread;
+    const uint32_t warp_leaf0 = chunk * kChunk + warp * kWarpLeaves;
+    const uint32_t leaf0 = warp_leaf0 + lane * kLeavesPerThread;
+    float2* wsm = sm + 3 * (warp * kWarpLeaves); // this warp's 128-node staging area
 
     // ---- faces of this thread's 4 consecutive leaves ----
     uint32_t idx[12];
@@ -446,11 +520,8 @@ __global__ void __launch_bounds__(kEmitThreads)
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-            const uint32_t* f = faces_in + 3ull * id[k];
-            const bool v = leaf0 + k < T;
-            idx[3 * k] = v ? __ldg(f) : 0u;
-            idx[3 * k + 1] = v ? __ldg(f + 1) : 0u;
-            idx[3 * k + 2] = v ? __ldg(f + 2) : 0u;
+            const uint4 f = (leaf0 + k < T) ? __ldg(faces_in4 + id[k]) : make_uint4(0, 0, 0, 0);
+            idx[3 * k] = f.x; idx[3 * k + 1] = f.y; idx[3 * k + 2] = f.z;
         }
         if (full)
         {
@@ -470,7 +541,7 @@ __global__ void __launch_bounds__(kEmitThreads)
     {
         if (full)
         {
-            const uint4* f4 = reinterpret_cast<const uint4*>(faces_in + 3ull * leaf0);
+            const uint4* f4 = reinterpret_cast<const uint4*>(faces_sorted + 3ull * leaf0);
             const uint4 a = ldg_stream_u4(f4), b = ldg_stream_u4(f4 + 1), c = ldg_stream_u4(f4 + 2);
             idx[0] = a.x; idx[1] = a.y; idx[2] = a.z; idx[3] = a.w;
             idx[4] = b.x; idx[5] = b.y; idx[6] = b.z; idx[7] = b.w;
@@ -479,91 +550,97 @@ __global__ void __launch_bounds__(kEmitThreads)
         else
         {
 #pragma unroll
-            for (int k = 0; k < 12; k++) idx[k] = (leaf0 + k / 3 < T) ? faces_in[3ull * leaf0 + k] : 0u;
+            for (int k = 0; k < 12; k++) idx[k] = (leaf0 + k / 3 < T) ? faces_sorted[3ull * leaf0 + k] : 0u;
         }
     }
 
     // ---- heights 0..2 in registers. A node at height h, position p exists iff p * 2^h < T. ----
+    float4 v[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) v[k] = __ldg(pos4 + idx[k]); // idx = 0 for missing leaves: harmless load
     Box leaf[4];
 #pragma unroll
     for (int k = 0; k < 4; k++)
     {
-        leaf[k] = Box{0, 0, 0, 0, 0, 0};
-        if (leaf0 + k < T)
-        {
-            leaf[k] = face_box(pos, idx[3 * k], idx[3 * k + 1], idx[3 * k + 2]);
-            stage_box(sm, sm_off(0) + tid * 4 + k, leaf[k]);
-        }
+        leaf[k] = box_of(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+        if (leaf0 + k < T) stage_box(wsm, lane * 4 + k, leaf[k]);
     }
-    Box h1[2];
-    h1[0] = (leaf0 + 1 < T) ? box_merge(leaf[0], leaf[1]) : leaf[0];
-    h1[1] = (leaf0 + 3 < T) ? box_merge(leaf[2], leaf[3]) : leaf[2];
-    if (leaf0 < T) stage_box(sm, sm_off(1) + tid * 2, h1[0]);
-    if (leaf0 + 2 < T) stage_box(sm, sm_off(1) + tid * 2 + 1, h1[1]);
-    Box cur = (leaf0 + 2 < T) ? box_merge(h1[0], h1[1]) : h1[0];
-    if (leaf0 < T) stage_box(sm, sm_off(2) + tid, cur);
+    const uint32_t warp_valid = (warp_leaf0 < T) ? min((uint32_t)kWarpLeaves, T - warp_leaf0) : 0u;
+    __syncwarp();
+    if (warp_valid)
+        warp_copy_out(nodes + 3ull * (level_offset(T, L, L) + warp_leaf0), wsm, 3 * warp_valid, lane);
+    __syncwarp();
 
-    // ---- heights 3..7 by warp shuffles: lane with (lane % 2^(h-2)) == 0 owns the height-h node ----
+    // internal nodes of the warp subtree, staged by height: slots [woff(h), woff(h) + (128 >> h)), h = 1..7
+    Box h1a = (leaf0 + 1 < T) ? box_merge(leaf[0], leaf[1]) : leaf[0];
+    Box h1b = (leaf0 + 3 < T) ? box_merge(leaf[2], leaf[3]) : leaf[2];
+    if (leaf0 < T) stage_box(wsm, woff(1) + lane * 2, h1a);
+    if (leaf0 + 2 < T) stage_box(wsm, woff(1) + lane * 2 + 1, h1b);
+    Box cur = (leaf0 + 2 < T) ? box_merge(h1a, h1b) : h1a;
+    if (leaf0 < T) stage_box(wsm, woff(2) + lane, cur);
 #pragma unroll
-    for (int h = 3; h <= 7; h++)
+    for (int h = 3; h <= kWarpLevels; h++)
     {
         const int delta = 1 << (h - 3);
         const Box right = shfl_down_box(cur, delta);
-        // right child = height h-1 node of thread tid+delta, first leaf = leaf0 + delta*4
+        // right child = height h-1 node owned by lane + delta, first leaf = leaf0 + delta * 4
         if (leaf0 + (uint32_t)delta * 4 < T) cur = box_merge(cur, right);
-        if ((lane & (2 * delta - 1)) == 0 && leaf0 < T) stage_box(sm, sm_off(h) + (tid >> (h - 2)), cur);
+        if ((lane & (2 * delta - 1)) == 0 && leaf0 < T) stage_box(wsm, woff(h) + (lane >> (h - 2)), cur);
     }
-    __syncthreads();
-
-    // ---- heights 8..10 across the 8 warps (warp 0 only; tiny) ----
-    if (tid < 32)
-    {
+    if (lane == 0 && warp_leaf0 < T) stage_box(s_top, warp, cur); // warp root = height 7
+    __syncwarp();
 #pragma unroll
-        for (int h = 8; h <= kChunkLevels; h++)
+    for (int h = 1; h <= kWarpLevels; h++)
+    {
+        if ((uint32_t)h > L) break;
+        const uint32_t first = warp_leaf0 >> h;
+        const uint32_t cnt = level_count(T, L, L - h);
+        if (first < cnt)
         {
-            const uint32_t n = kChunk >> h; // nodes at this height in the chunk
-            if (tid < n)
-            {
-                const uint32_t first_leaf = chunk * kChunk + (tid << h);
-                if (first_leaf < T)
-                {
-                    Box b = unstage_box(sm, sm_off(h - 1) + 2 * tid);
-                    if (first_leaf + (1u << (h - 1)) < T) b = box_merge(b, unstage_box(sm, sm_off(h - 1) + 2 * tid + 1));
-                    stage_box(sm, sm_off(h) + tid, b);
-                }
-            }
-            __syncwarp();
+            const uint32_t n = min((uint32_t)(kWarpLeaves >> h), cnt - first);
+            warp_copy_out(nodes + 3ull * (level_offset(T, L, L - h) + first), wsm + 3 * woff(h), 3 * n, lane);
         }
     }
     __syncthreads();
 
-    // ---- coalesced stores: the chunk's nodes of one height are one contiguous slice of that level ----
-    const uint32_t hmax = min((uint32_t)kChunkLevels, L);
-    for (uint32_t h = 0; h <= hmax; h++)
+    // ---- heights 8..10 across the 8 warps (first lanes of warp 0; tiny) ----
+    if (warp == 0)
     {
-        const uint32_t l = L - h;
-        const uint32_t per = kChunk >> h;
-        const uint32_t first = chunk * per;
-        const uint32_t cnt = level_count(T, L, l);
-        if (first >= cnt) break;
-        const uint32_t n = min(per, cnt - first);
-        float2* dst = nodes + 3ull * (level_offset(T, L, l) + first);
-        const float2* src = sm + 3 * sm_off(h);
-        for (uint32_t i = tid; i < 3 * n; i += kEmitThreads) dst[i] = src[i];
+        // s_top slots: height 7: [0,8), 8: [8,12), 9: [12,14), 10: [14,15)
+        int src = 0, dstb = 8;
+#pragma unroll
+        for (int h = kWarpLevels + 1; h <= kChunkLevels; h++)
+        {
+            const uint32_t n = kChunk >> h;
+            if ((uint32_t)h <= L && lane < n)
+            {
+                const uint32_t first_leaf = chunk * kChunk + (lane << h);
+                if (first_leaf < T)
+                {
+                    Box b = unstage_box(s_top, src + 2 * lane);
+                    if (first_leaf + (1u << (h - 1)) < T) b = box_merge(b, unstage_box(s_top, src + 2 * lane + 1));
+                    stage_box(s_top, dstb + lane, b);
+                    store_box(nodes, level_offset(T, L, L - h) + (chunk * kChunk >> h) + lane, b);
+                }
+            }
+            src = dstb;
+            dstb += n;
+            __syncwarp();
+        }
     }
 
     // ---- the last CTA to retire finishes levels above the chunk roots ----
     if (L <= (uint32_t)kChunkLevels) return; // the single chunk already holds the root
-    __threadfence();
     __syncthreads();
     if (tid == 0)
     {
+        __threadfence(); // cumulative: publishes the chunk's stores observed through the CTA barrier above
         const uint32_t prev = atomicAdd(done_counter, 1u);
         s_last = (prev == gridDim.x - 1);
+        if (s_last) __threadfence();
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     finish_top(nodes, sm, T, L, L - kChunkLevels);
     if (tid == 0) *done_counter = 0; // re-arm for the next launch on this tree
 }
@@ -573,33 +650,53 @@ __global__ void __launch_bounds__(kEmitThreads)
 // (third/glm/detail/type_mat4x4.inl:561-572), never contracted. Replaces transform_vec4_kernel
 // (src/cuda/transform.cu:35-40) and its H2D/D2H round trip.
 // =================================================================================================
-__global__ void __launch_bounds__(256) transform_kernel(float* __restrict__ pos, uint32_t V, Mat4 M)
+__global__ void __launch_bounds__(256) transform_kernel(float4* __restrict__ pos4, uint32_t V, Mat4 M)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
-    float* p = pos + 3ull * i;
-    const float x = p[0], y = p[1], z = p[2];
+    const float4 p = pos4[i];
+    float r[3];
 #pragma unroll
-    for (int r = 0; r < 3; r++)
+    for (int k = 0; k < 3; k++)
     {
-        const float add0 = __fadd_rn(__fmul_rn(M.m[0 + r], x), __fmul_rn(M.m[4 + r], y));
-        const float add1 = __fadd_rn(__fmul_rn(M.m[8 + r], z), __fmul_rn(M.m[12 + r], 1.0f));
-        p[r] = __fadd_rn(add0, add1);
+        const float add0 = __fadd_rn(__fmul_rn(M.m[0 + k], p.x), __fmul_rn(M.m[4 + k], p.y));
+        const float add1 = __fadd_rn(__fmul_rn(M.m[8 + k], p.z), __fmul_rn(M.m[12 + k], 1.0f));
+        r[k] = __fadd_rn(add0, add1);
     }
+    pos4[i] = make_float4(r[0], r[1], r[2], 1.0f);
 }
 
 // =================================================================================================
 // Launchers
 // =================================================================================================
-cudaError_t launch_morton_hist(const uint32_t* faces, const float* pos, uint32_t T, const MeshAabb& mesh,
+cudaError_t launch_pack_positions(const float* xyz, float4* pos4, uint32_t V, cudaStream_t s)
+{
+    pack_pos_kernel<<<(V + 255) / 256, 256, 0, s>>>(xyz, pos4, V);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_positions(const float4* pos4, float* xyz, uint32_t V, cudaStream_t s)
+{
+    unpack_pos_kernel<<<(V + 255) / 256, 256, 0, s>>>(pos4, xyz, V);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_faces(const uint32_t* f3, uint4* faces4, uint32_t T, cudaStream_t s)
+{
+    pack_faces_kernel<<<(T + 255) / 256, 256, 0, s>>>(f3, faces4, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_morton_hist(const uint4* faces4, const float4* pos4, uint32_t T, const MeshAabb& mesh,
                                uint32_t* keys, uint32_t* hist, cudaStream_t s)
 {
-    const uint32_t groups = (T + 3) / 4;
-    uint32_t blocks = (groups + 255) / 256;
-    const uint32_t cap = kNumSMsB200 * 8;
+    const uint32_t tile = 256 * kMortonFacesPerThread;
+    uint32_t blocks = (T + tile - 1) / tile;
+    const uint32_t cap = kNumSMsB200 * 5; // 48 registers -> 5 resident CTAs per SM
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    morton_hist_kernel<kRadixBits, kRadixPasses><<<blocks, 256, 0, s>>>(faces, pos, T, mesh, keys, hist);
+    if (hist)
+        morton_hist_kernel<kRadixBits, kRadixPasses, true><<<blocks, 256, 0, s>>>(faces4, pos4, T, mesh, keys, hist);
+    else
+        morton_hist_kernel<kRadixBits, kRadixPasses, false><<<blocks, 256, 0, s>>>(faces4, pos4, T, mesh, keys, hist);
     return cudaGetLastError();
 }
 
@@ -625,24 +722,31 @@ cudaError_t tree_emit_configure()
                                 (int)kEmitSmemBytes);
 }
 
-cudaError_t launch_tree_emit(bool build, const uint32_t* faces_in, const uint32_t* perm, uint32_t* faces_sorted,
-                             const float* pos, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s)
+cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
+                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s)
 {
     const uint32_t L = ceil_log2_u32(T);
     const uint32_t chunks = (T + kChunk - 1) / kChunk;
     if (build)
         tree_emit_kernel<true><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            faces_in, perm, faces_sorted, pos, reinterpret_cast<float2*>(nodes), T, L, done_counter);
+            faces_in4, perm, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, done_counter);
     else
         tree_emit_kernel<false><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            faces_in, nullptr, nullptr, pos, reinterpret_cast<float2*>(nodes), T, L, done_counter);
+            nullptr, nullptr, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, done_counter);
     return cudaGetLastError();
 }
 
-cudaError_t launch_transform(float* pos, uint32_t V, const Mat4& M, cudaStream_t s)
+#ifdef OIBVH_PROFILE
+extern "C" int oibvh_debug_sort_profile(unsigned long long* out /* 4*2*8 */)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_sort_prof, sizeof(g_sort_prof));
+}
+#endif
+
+cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream_t s)
 {
     if (V == 0) return cudaSuccess;
-    transform_kernel<<<(V + 255) / 256, 256, 0, s>>>(pos, V, M);
+    transform_kernel<<<(V + 255) / 256, 256, 0, s>>>(pos4, V, M);
     return cudaGetLastError();
 }
 
