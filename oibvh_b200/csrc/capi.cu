@@ -208,13 +208,13 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
         (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
         (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
         (rc = dev_alloc(&t->vals_b, T4)) || (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
-        (rc = dev_alloc(&t->done_counter, 1)))
+        (rc = dev_alloc(&t->done_counter, emit_counter_words(T))))
     {
         tree_free(t);
         delete t;
         return rc;
     }
-    cudaError_t e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t), ctx->stream);
+    cudaError_t e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t) * emit_counter_words(T), ctx->stream);
     if (e != cudaSuccess)
     {
         tree_free(t);

@@ -75,20 +75,18 @@ __device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        __threadfence();
-        atomicAdd(counters + CTR_BARRIER, 1u);
+        // release-arrive / acquire-poll (see grid_sync in common.cuh)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + CTR_BARRIER) : "memory");
         const uint32_t target = generation * gridDim.x;
         uint32_t spins = 0;
         while (ld_acquire_gpu(counters + CTR_BARRIER) < target)
         {
-            __nanosleep(32);
-            if (++spins > (1u << 24))
+            if (++spins > (1u << 26))
             {
                 atomicOr(counters + CTR_OVERFLOW, 8u);
                 break;
             }
         }
-        __threadfence();
         s_value = __ldcg(read_after);
     }
     __syncthreads();

@@ -190,20 +190,19 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // release-arrive / acquire-poll: the release is cumulative over the CTA barrier above, the acquire orders
+        // everything after the barrier below -- no separate membar round trips
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         const uint32_t target = generation * gridDim.x;
         uint32_t spins = 0;
         while (ld_acquire_gpu(counter) < target)
         {
-            __nanosleep(32);
-            if (++spins > (1u << 24))
+            if (++spins > (1u << 26))
             {
                 atomicOr(fail_flag, 1u);
                 break;
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }

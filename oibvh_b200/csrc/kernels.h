@@ -40,6 +40,8 @@ size_t coop_sort_ctl_words();
 cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
                              uint32_t* ctl, cudaStream_t s);
 cudaError_t tree_emit_configure();
+// arrival counters of the hierarchical top-of-tree completion (zeroed once; the kernel re-arms them)
+size_t emit_counter_words(uint32_t T);
 cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
                              const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s);
 cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream_t s);

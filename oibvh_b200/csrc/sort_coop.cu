@@ -22,20 +22,34 @@ constexpr int kCoopIptMax = 8;
 constexpr int kCoopRadix = 1 << kRadixBits; // 256
 constexpr int kCoopTileMax = kCoopThreads * kCoopIptMax; // 4096 keys per CTA
 constexpr int kCoopRowSeg = 10;                          // row scan: entries per lane -> grids up to 320 CTAs
-static_assert(kCoopWarps * kCoopRadix <= kCoopTileMax, "peer masks alias the key staging area");
+// two CTAs of 512 threads per SM measured faster than one of 1024 (shorter block-level phases)
 
 // control block (uint32 words): [0] barrier counter, [1] failure flag, [64, 64+256) digit totals, [512, ...) counts
 constexpr int kCoopCtlTotals = 64;
 constexpr int kCoopCtlMat = 512;
 
+#ifdef OIBVH_PROFILE
+__device__ unsigned long long g_coop_prof[4][2][12]; // [pass][first/last cta][stamp]
+#define COOP_STAMP(k)                                                                                              \
+    do                                                                                                             \
+    {                                                                                                              \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                                  \
+            g_coop_prof[pass][blockIdx.x == 0 ? 0 : 1][k] = clock64();                                             \
+    } while (0)
+extern "C" int oibvh_debug_coop_profile(unsigned long long* out)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_coop_prof, sizeof(g_coop_prof));
+}
+#else
+#define COOP_STAMP(k)
+#endif
+
 struct CoopSmem
 {
-    uint32_t hist[kCoopWarps][kCoopRadix]; // per-warp digit counts, then warp-exclusive offsets
-    uint32_t keys[kCoopTileMax];           // ranking phase: per-warp peer masks ; reorder phase: keys by slot
-    uint32_t vals[kCoopTileMax];
-    uint32_t digit_base[kCoopRadix];
+    uint2 rank_tab[kCoopWarps][kCoopRadix]; // ranking: (.x running count, .y peer mask); afterwards .x = slot base
+    uint2 kv[kCoopTileMax];                 // reorder phase: (key, value) by slot
     uint32_t global_base[kCoopRadix];
-    uint32_t scan[kCoopWarps];
+    uint32_t scan[16];
 };
 
 __global__ void __launch_bounds__(kCoopThreads, 2)
@@ -44,7 +58,6 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CoopSmem& sm = *reinterpret_cast<CoopSmem*>(smem_raw);
-    uint32_t(*s_mask)[kCoopRadix] = reinterpret_cast<uint32_t(*)[kCoopRadix]>(sm.keys);
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint32_t cta = blockIdx.x, G = gridDim.x;
@@ -61,6 +74,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
     {
         const uint32_t shift = pass * kRadixBits;
         constexpr uint32_t MASK = kCoopRadix - 1;
+        COOP_STAMP(0);
         // ---- load this CTA's chunk (written by other SMs in the previous pass: through L2) ----
         uint32_t key[kCoopIptMax], val[kCoopIptMax];
         uint16_t rank[kCoopIptMax];
@@ -72,16 +86,12 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             key[j] = valid ? __ldcg(kin + i) : 0xffffffffu;
             val[j] = (valid && vin) ? __ldcg(vin + i) : i; // first pass: the value is the face id
         }
-        for (int i = tid; i < kCoopWarps * kCoopRadix; i += kCoopThreads)
-        {
-            (&sm.hist[0][0])[i] = 0;
-            (&s_mask[0][0])[i] = 0;
-        }
+        for (int i = tid; i < kCoopWarps * kCoopRadix; i += kCoopThreads) (&sm.rank_tab[0][0])[i] = make_uint2(0u, 0u);
         __syncthreads();
 
+        COOP_STAMP(1);
         // ---- stable in-warp ranking with shared-memory peer masks (see onesweep_pass_kernel) ----
-        uint32_t* my_hist = sm.hist[warp];
-        uint32_t* my_mask = s_mask[warp];
+        uint2* my_tab = sm.rank_tab[warp];
         const uint32_t lane_bit = 1u << lane;
 #pragma unroll
         for (int j = 0; j < kCoopIptMax; j++)
@@ -91,27 +101,20 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
                 const uint32_t i = warp_base + j * 32 + lane;
                 const bool valid = i < T;
                 const uint32_t d = (key[j] >> shift) & MASK;
-                if (valid) atomicOr(my_mask + d, lane_bit);
+                if (valid) atomicOr(&my_tab[d].y, lane_bit);
                 __syncwarp();
-                uint32_t peers = 0, before = 0;
-                if (valid)
-                {
-                    peers = my_mask[d];
-                    before = my_hist[d];
-                }
-                const uint32_t lower = __popc(peers & lanemask_lt());
-                rank[j] = (uint16_t)(before + lower);
+                uint2 e = make_uint2(0u, 0u);
+                if (valid) e = my_tab[d]; // (count before this step, peers of this step)
+                const uint32_t lower = __popc(e.y & lanemask_lt());
+                rank[j] = (uint16_t)(e.x + lower);
                 __syncwarp();
-                if (valid && lower == 0)
-                {
-                    my_hist[d] = before + __popc(peers);
-                    my_mask[d] = 0;
-                }
+                if (valid && lower == 0) my_tab[d] = make_uint2(e.x + __popc(e.y), 0u); // lowest lane closes the group
                 __syncwarp();
             }
         }
         __syncthreads();
 
+        COOP_STAMP(2);
         // ---- per digit: warp-exclusive offsets, CTA count -> counts[digit][cta] ----
         uint32_t cta_count = 0;
         if (tid < kCoopRadix)
@@ -120,19 +123,22 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
 #pragma unroll
             for (int w = 0; w < kCoopWarps; w++)
             {
-                const uint32_t c = sm.hist[w][tid];
-                sm.hist[w][tid] = run;
+                const uint32_t c = sm.rank_tab[w][tid].x;
+                sm.rank_tab[w][tid].x = run;
                 run += c;
             }
             cta_count = run;
             mat[(size_t)tid * G + cta] = cta_count;
         }
+        COOP_STAMP(3);
         grid_sync(ctl, ++gen, ctl + 1);
+        COOP_STAMP(4);
 
         // ---- one warp scans each digit row (exclusive prefix over CTAs) and records the row total ----
-        if (warp == 0)
         {
-            for (uint32_t r = cta; r < (uint32_t)kCoopRadix; r += G)
+            // rows cta, cta + G, ... : one warp each
+            const uint32_t r = cta + warp * G;
+            if (r < (uint32_t)kCoopRadix)
             {
                 uint32_t* row = mat + (size_t)r * G;
                 uint32_t v[kCoopRowSeg];
@@ -162,7 +168,9 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
                 if (lane == 31) totals[r] = inc;
             }
         }
+        COOP_STAMP(5);
         grid_sync(ctl, ++gen, ctl + 1);
+        COOP_STAMP(6);
 
         // ---- global base of every digit for this CTA ----
         uint32_t col = 0, tot = 0;
@@ -171,15 +179,48 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             col = __ldcg(mat + (size_t)tid * G + cta);
             tot = __ldcg(totals + tid);
         }
-        const uint32_t bin_start = block_exclusive_scan<kCoopThreads>(tot, sm.scan);
-        const uint32_t digit_base = block_exclusive_scan<kCoopThreads>(cta_count, sm.scan);
+        // exclusive scans over the 256 digits of (row totals -> bin start) and (CTA counts -> slot base), fused:
+        // warp scans of both values, then the 8 warp totals
+        uint32_t inc_t = tot, inc_c = cta_count;
         if (tid < kCoopRadix)
         {
-            sm.digit_base[tid] = digit_base;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, inc_t, o), b = __shfl_up_sync(0xffffffffu, inc_c, o);
+                if (lane >= (uint32_t)o)
+                {
+                    inc_t += a;
+                    inc_c += b;
+                }
+            }
+            if (lane == 31)
+            {
+                sm.scan[warp] = inc_t;
+                sm.scan[8 + warp] = inc_c;
+            }
+        }
+        __syncthreads();
+        if (tid < kCoopRadix)
+        {
+            uint32_t base_t = 0, base_c = 0;
+#pragma unroll
+            for (int w = 0; w < kCoopRadix / 32; w++)
+                if ((uint32_t)w < warp)
+                {
+                    base_t += sm.scan[w];
+                    base_c += sm.scan[8 + w];
+                }
+            const uint32_t bin_start = base_t + inc_t - tot;
+            const uint32_t digit_base = base_c + inc_c - cta_count;
             sm.global_base[tid] = bin_start + col - digit_base;
+            // fold the CTA-level digit base into the per-warp offsets: slot = rank_tab[warp][d].x + rank
+#pragma unroll
+            for (int w = 0; w < kCoopWarps; w++) sm.rank_tab[w][tid].x += digit_base;
         }
         __syncthreads();
 
+        COOP_STAMP(7);
         // ---- reorder inside the chunk through shared memory, then write digit runs coalesced ----
 #pragma unroll
         for (int j = 0; j < kCoopIptMax; j++)
@@ -188,9 +229,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             if ((uint32_t)j < ipt && i < T)
             {
                 const uint32_t d = (key[j] >> shift) & MASK;
-                const uint32_t slot = sm.digit_base[d] + my_hist[d] + rank[j];
-                sm.keys[slot] = key[j];
-                sm.vals[slot] = val[j];
+                sm.kv[my_tab[d].x + rank[j]] = make_uint2(key[j], val[j]);
             }
         }
         __syncthreads();
@@ -200,13 +239,15 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             const uint32_t s = tid + k * kCoopThreads;
             if (s < cta_valid)
             {
-                const uint32_t kk = sm.keys[s];
-                const uint32_t dst = sm.global_base[(kk >> shift) & MASK] + s;
-                kout[dst] = kk;
-                vout[dst] = sm.vals[s];
+                const uint2 e = sm.kv[s];
+                const uint32_t dst = sm.global_base[(e.x >> shift) & MASK] + s;
+                kout[dst] = e.x;
+                vout[dst] = e.y;
             }
         }
+        COOP_STAMP(8);
         if (pass + 1 < kRadixPasses) grid_sync(ctl, ++gen, ctl + 1);
+        COOP_STAMP(9);
         // ping-pong
         uint32_t* nk = kout;
         uint32_t* nv = vout;

@@ -367,6 +367,12 @@ __global__ void __launch_bounds__(1 << RADIX_BITS)
 // CTA:    heights 8..10 from the 8 warp roots
 // grid:   the last CTA to retire reduces the chunk roots to the tree root (finish_top)
 // =================================================================================================
+struct LevelTable
+{
+    uint32_t off[32]; // first node of level l in the node array
+    uint32_t cnt[32]; // nodes kept at level l
+};
+
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
 constexpr int kLeavesPerThread = 4;
@@ -374,7 +380,6 @@ constexpr int kWarpLeaves = 32 * kLeavesPerThread;      // 128
 constexpr int kChunk = kEmitThreads * kLeavesPerThread; // 1024 leaves
 constexpr int kChunkLevels = 10;                        // log2(kChunk)
 constexpr int kWarpLevels = 7;                          // log2(kWarpLeaves)
-constexpr int kTopSmemNodes = 512;                      // finish_top switches to shared memory at this width
 
 // slot of the first height-h node inside a warp's staging area (h = 1..7): 0, 64, 96, 112, 120, 124, 126
 __device__ __forceinline__ constexpr int woff(int h) { return kWarpLeaves - (2 * kWarpLeaves >> h); }
@@ -429,71 +434,24 @@ __device__ __forceinline__ void warp_copy_out(float2* __restrict__ dst, const fl
     if (lane == 0 && ((n8 - head) & 1u)) dst[n8 - 1] = src[n8 - 1];
 }
 
-// Levels [0, top_level) of the tree, given that level `top_level` is complete in global memory.
-// Run by one CTA (the last one to finish its chunk). `sm` holds at least 1.5 * kTopSmemNodes nodes.
-__device__ void finish_top(float2* __restrict__ nodes, float2* sm, uint32_t T, uint32_t L, uint32_t top_level)
-{
-    uint32_t l = top_level;
-    // wide levels: straight through L2
-    while (l > 0 && level_count(T, L, l) > (uint32_t)kTopSmemNodes)
-    {
-        const uint32_t cnt_c = level_count(T, L, l), cnt_p = level_count(T, L, l - 1);
-        const uint32_t off_c = level_offset(T, L, l), off_p = level_offset(T, L, l - 1);
-        for (uint32_t p = threadIdx.x; p < cnt_p; p += blockDim.x)
-        {
-            Box b = load_box_cg(nodes, off_c + 2 * p);
-            if (2 * p + 1 < cnt_c) b = box_merge(b, load_box_cg(nodes, off_c + 2 * p + 1));
-            store_box(nodes, off_p + p, b);
-        }
-        __threadfence_block();
-        __syncthreads();
-        l--;
-    }
-    if (l == 0) return;
-    // narrow levels: shared memory
-    float2* cur = sm;
-    float2* nxt = sm + 3 * kTopSmemNodes;
-    uint32_t cnt_c = level_count(T, L, l);
-    {
-        const float2* src = nodes + 3ull * level_offset(T, L, l);
-        for (uint32_t i = threadIdx.x; i < 3 * cnt_c; i += blockDim.x) cur[i] = __ldcg(src + i);
-    }
-    __syncthreads();
-    while (l > 0)
-    {
-        const uint32_t cnt_p = level_count(T, L, l - 1);
-        const uint32_t off_p = level_offset(T, L, l - 1);
-        for (uint32_t p = threadIdx.x; p < cnt_p; p += blockDim.x)
-        {
-            Box b = unstage_box(cur, 2 * p);
-            if (2 * p + 1 < cnt_c) b = box_merge(b, unstage_box(cur, 2 * p + 1));
-            stage_box(nxt, p, b);
-            store_box(nodes, off_p + p, b);
-        }
-        __syncthreads();
-        float2* t = cur; cur = nxt; nxt = t;
-        cnt_c = cnt_p;
-        l--;
-    }
-}
-
-// shared memory: per-warp staging, 8 x 128 nodes x 24 B = 24 KB, reused by finish_top (512 + 256 nodes)
+// shared memory: per-warp staging, 8 x 128 nodes x 24 B = 24 KB
 constexpr int kEmitStageNodes = kEmitWarps * kWarpLeaves; // 1024
 constexpr size_t kEmitSmemBytes = (size_t)kEmitStageNodes * 24;
-static_assert(kTopSmemNodes + kTopSmemNodes / 2 <= kEmitStageNodes, "finish_top staging must fit");
 
+#ifndef OIBVH_EMIT_MINB
+#define OIBVH_EMIT_MINB 5
+#endif
 template <bool BUILD>
-__global__ void __launch_bounds__(kEmitThreads, 5)
+__global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
     tree_emit_kernel(const uint4* __restrict__ faces_in4,     // BUILD: input-order faces (16-byte records)
                      const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
                      uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
                      const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
-                     uint32_t* done_counter)
+                     const LevelTable lv, uint32_t* done_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     __shared__ float2 s_top[3 * 16]; // heights 7..10 of the chunk: 8 + 4 + 2 + 1 nodes
-    __shared__ bool s_last;
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint32_t chunk = blockIdx.x;
@@ -565,19 +523,25 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
         leaf[k] = box_of(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
         if (leaf0 + k < T) stage_box(wsm, lane * 4 + k, leaf[k]);
     }
+    // Level slices come from the host-built table (lv.off / lv.cnt by level), not from 64-bit arithmetic here.
+    // Heights 0..2 (87.5 % of the bytes) go through the warp staging area and leave as 128-bit coalesced stores;
+    // the few nodes of heights 3..7 are stored directly by the lane that owns them.
     const uint32_t warp_valid = (warp_leaf0 < T) ? min((uint32_t)kWarpLeaves, T - warp_leaf0) : 0u;
     __syncwarp();
-    if (warp_valid)
-        warp_copy_out(nodes + 3ull * (level_offset(T, L, L) + warp_leaf0), wsm, 3 * warp_valid, lane);
+    if (warp_valid) warp_copy_out(nodes + 3ull * (lv.off[L] + warp_leaf0), wsm, 3 * warp_valid, lane);
     __syncwarp();
 
-    // internal nodes of the warp subtree, staged by height: slots [woff(h), woff(h) + (128 >> h)), h = 1..7
     Box h1a = (leaf0 + 1 < T) ? box_merge(leaf[0], leaf[1]) : leaf[0];
     Box h1b = (leaf0 + 3 < T) ? box_merge(leaf[2], leaf[3]) : leaf[2];
-    if (leaf0 < T) stage_box(wsm, woff(1) + lane * 2, h1a);
-    if (leaf0 + 2 < T) stage_box(wsm, woff(1) + lane * 2 + 1, h1b);
+    if (leaf0 < T) stage_box(wsm, lane * 2, h1a);              // height 1: slots [0, 64)
+    if (leaf0 + 2 < T) stage_box(wsm, lane * 2 + 1, h1b);
     Box cur = (leaf0 + 2 < T) ? box_merge(h1a, h1b) : h1a;
-    if (leaf0 < T) stage_box(wsm, woff(2) + lane, cur);
+    if (leaf0 < T) stage_box(wsm, 64 + lane, cur);              // height 2: slots [64, 96)
+    __syncwarp();
+    if (L >= 1 && warp_valid)
+        warp_copy_out(nodes + 3ull * (lv.off[L - 1] + (warp_leaf0 >> 1)), wsm, 3 * ((warp_valid + 1) >> 1), lane);
+    if (L >= 2 && warp_valid)
+        warp_copy_out(nodes + 3ull * (lv.off[L - 2] + (warp_leaf0 >> 2)), wsm + 3 * 64, 3 * ((warp_valid + 3) >> 2), lane);
 #pragma unroll
     for (int h = 3; h <= kWarpLevels; h++)
     {
@@ -585,22 +549,10 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
         const Box right = shfl_down_box(cur, delta);
         // right child = height h-1 node owned by lane + delta, first leaf = leaf0 + delta * 4
         if (leaf0 + (uint32_t)delta * 4 < T) cur = box_merge(cur, right);
-        if ((lane & (2 * delta - 1)) == 0 && leaf0 < T) stage_box(wsm, woff(h) + (lane >> (h - 2)), cur);
+        if ((lane & (2 * delta - 1)) == 0 && leaf0 < T && (uint32_t)h <= L)
+            store_box(nodes, lv.off[L - h] + (leaf0 >> h), cur);
     }
     if (lane == 0 && warp_leaf0 < T) stage_box(s_top, warp, cur); // warp root = height 7
-    __syncwarp();
-#pragma unroll
-    for (int h = 1; h <= kWarpLevels; h++)
-    {
-        if ((uint32_t)h > L) break;
-        const uint32_t first = warp_leaf0 >> h;
-        const uint32_t cnt = level_count(T, L, L - h);
-        if (first < cnt)
-        {
-            const uint32_t n = min((uint32_t)(kWarpLeaves >> h), cnt - first);
-            warp_copy_out(nodes + 3ull * (level_offset(T, L, L - h) + first), wsm + 3 * woff(h), 3 * n, lane);
-        }
-    }
     __syncthreads();
 
     // ---- heights 8..10 across the 8 warps (first lanes of warp 0; tiny) ----
@@ -620,7 +572,7 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
                     Box b = unstage_box(s_top, src + 2 * lane);
                     if (first_leaf + (1u << (h - 1)) < T) b = box_merge(b, unstage_box(s_top, src + 2 * lane + 1));
                     stage_box(s_top, dstb + lane, b);
-                    store_box(nodes, level_offset(T, L, L - h) + (chunk * kChunk >> h) + lane, b);
+                    store_box(nodes, lv.off[L - h] + (chunk * kChunk >> h) + lane, b);
                 }
             }
             src = dstb;
@@ -629,20 +581,58 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
         }
     }
 
-    // ---- the last CTA to retire finishes levels above the chunk roots ----
+    // ---- levels above the chunk roots: hierarchical completion, 32 nodes (5 levels) per stage ----
+    // Every group of 32 consecutive completed nodes has an arrival counter; the warp whose arrival completes a
+    // group reduces it with shuffles, which completes one node 5 levels up, and so on to the root. No CTA waits:
+    // warps 1..7 are done, warp 0 pays one fence + one atomic, and the tail is a few warp-level stages.
     if (L <= (uint32_t)kChunkLevels) return; // the single chunk already holds the root
-    __syncthreads();
-    if (tid == 0)
+#ifdef OIBVH_EXP_NOTOP
+    return;
+#endif
+    __syncthreads(); // every store of this CTA has been issued
+    if (warp != 0) return;
+    uint32_t level = L - kChunkLevels, pos = chunk;
+    uint32_t* ctr = done_counter;
+    while (level > 0)
     {
-        __threadfence(); // cumulative: publishes the chunk's stores observed through the CTA barrier above
-        const uint32_t prev = atomicAdd(done_counter, 1u);
-        s_last = (prev == gridDim.x - 1);
-        if (s_last) __threadfence();
+        const uint32_t n = lv.cnt[level];
+        const uint32_t group = pos >> 5, first = group << 5;
+        const uint32_t members = min(32u, n - first);
+        uint32_t last = 0;
+        if (lane == 0)
+        {
+            __threadfence(); // cumulative over the CTA barrier / the previous stage's stores
+            const uint32_t prev = atomicAdd(ctr + group, 1u);
+            last = (prev == members - 1);
+            if (last)
+            {
+                ctr[group] = 0; // re-arm for the next launch on this tree
+                __threadfence();
+            }
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        Box cur = Box{0, 0, 0, 0, 0, 0};
+        if (lane < members) cur = load_box_cg(nodes, lv.off[level] + first + lane);
+        uint32_t l = level;
+#pragma unroll
+        for (int s5 = 0; s5 < 5; s5++)
+        {
+            if (l == 0) break; // warp-uniform
+            const Box right = shfl_down_box(cur, 1 << s5);
+            const uint32_t child = (first >> s5) + (lane >> s5); // position at level l of this lane's node
+            const bool owner = (lane & ((2u << s5) - 1)) == 0;
+            if (owner && child < lv.cnt[l])
+            {
+                if (child + 1 < lv.cnt[l]) cur = box_merge(cur, right);
+                store_box(nodes, lv.off[l - 1] + (child >> 1), cur);
+            }
+            l--;
+        }
+        ctr += (n + 31) >> 5; // counters of the next stage follow this stage's
+        pos = group;
+        level = l;
     }
-    __syncthreads();
-    if (!s_last) return;
-    finish_top(nodes, sm, T, L, L - kChunkLevels);
-    if (tid == 0) *done_counter = 0; // re-arm for the next launch on this tree
 }
 
 // =================================================================================================
@@ -722,17 +712,34 @@ cudaError_t tree_emit_configure()
                                 (int)kEmitSmemBytes);
 }
 
+size_t emit_counter_words(uint32_t T)
+{
+    size_t n = (T + kChunk - 1) / kChunk, words = 0;
+    while (n > 1)
+    {
+        n = (n + 31) / 32;
+        words += n;
+    }
+    return words + 32;
+}
+
 cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
                              const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s)
 {
     const uint32_t L = ceil_log2_u32(T);
     const uint32_t chunks = (T + kChunk - 1) / kChunk;
+    LevelTable lv;
+    for (uint32_t l = 0; l < 32; l++)
+    {
+        lv.off[l] = l <= L ? level_offset(T, L, l) : 0u;
+        lv.cnt[l] = l <= L ? level_count(T, L, l) : 0u;
+    }
     if (build)
         tree_emit_kernel<true><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            faces_in4, perm, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, done_counter);
+            faces_in4, perm, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter);
     else
         tree_emit_kernel<false><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            nullptr, nullptr, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, done_counter);
+            nullptr, nullptr, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter);
     return cudaGetLastError();
 }
 
