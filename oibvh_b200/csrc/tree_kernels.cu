@@ -434,34 +434,78 @@ __device__ __forceinline__ void warp_copy_out(float2* __restrict__ dst, const fl
     if (lane == 0 && ((n8 - head) & 1u)) dst[n8 - 1] = src[n8 - 1];
 }
 
-// shared memory: per-warp staging, 8 x 128 nodes x 24 B = 24 KB
-constexpr int kEmitStageNodes = kEmitWarps * kWarpLeaves; // 1024
-constexpr size_t kEmitSmemBytes = (size_t)kEmitStageNodes * 24;
+// shared memory: per-warp staging areas for heights 0, 1, 2 (3072 + 1536 + 768 B, each with 16 B of slack for the
+// alignment phase), 5440 B per warp, 42.5 KB per CTA
+constexpr int kWarpStageBytes = 3072 + 16 + 1536 + 16 + 768 + 16 + 16;
+static_assert(kWarpStageBytes % 16 == 0, "per-warp staging must keep 16-byte alignment");
+constexpr size_t kEmitSmemBytes = (size_t)kEmitWarps * kWarpStageBytes;
 
-#ifndef OIBVH_EMIT_MINB
-#define OIBVH_EMIT_MINB 5
-#endif
-template <bool BUILD>
-__global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
-    tree_emit_kernel(const uint4* __restrict__ faces_in4,     // BUILD: input-order faces (16-byte records)
-                     const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
-                     uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
-                     const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
-                     const LevelTable lv, uint32_t* done_counter)
+// ---- TMA bulk store of a level slice (full chunks): one elected lane copies the warp's staged nodes to global ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* sm = reinterpret_cast<float2*>(smem_raw);
-    __shared__ float2 s_top[3 * 16]; // heights 7..10 of the chunk: 8 + 4 + 2 + 1 nodes
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const uint32_t chunk = blockIdx.x;
-    const uint32_t warp_leaf0 = chunk * kChunk + warp * kWarpLeaves;
+// Issue the copy of `bytes` staged bytes to gdst (8-byte aligned). The staging area was filled at offset mis * 8
+// (mis = 1 iff gdst is not 16-byte aligned) so that source and destination share their 16-byte phase: the aligned
+// interior goes out as one bulk copy, the 8-byte head/tail of a misaligned slice as plain stores. Lane 0 only.
+__device__ __forceinline__ void slice_store(float2* gdst, const float2* stage /*16B aligned*/, uint32_t bytes, uint32_t mis)
+{
+    if (mis == 0)
+        bulk_store(gdst, stage, bytes);
+    else
+    {
+        gdst[0] = stage[1];
+        bulk_store(gdst + 1, stage + 2, bytes - 16);
+        gdst[bytes / 8 - 1] = stage[bytes / 8];
+    }
+}
+
+// write N floats (N % 4 == 0) held in registers to shared memory at `lane_base + mis * 8` bytes, lane_base 16-byte
+// aligned: 128-bit stores, with an 8-byte head and tail when mis = 1
+template <int N>
+__device__ __forceinline__ void stage_floats(float2* lane_base, const float (&f)[N], uint32_t mis)
+{
+    if (mis == 0)
+    {
+        float4* d = reinterpret_cast<float4*>(lane_base);
+#pragma unroll
+        for (int q = 0; q < N / 4; q++) d[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    }
+    else
+    {
+        lane_base[1] = make_float2(f[0], f[1]);
+        float4* d = reinterpret_cast<float4*>(lane_base + 2);
+#pragma unroll
+        for (int q = 0; q < N / 4 - 1; q++)
+            d[q] = make_float4(f[4 * q + 2], f[4 * q + 3], f[4 * q + 4], f[4 * q + 5]);
+        lane_base[N / 2] = make_float2(f[N - 2], f[N - 1]);
+    }
+}
+__device__ __forceinline__ void box_floats(const Box& b, float* f)
+{
+    f[0] = b.lx; f[1] = b.ly; f[2] = b.lz; f[3] = b.hx; f[4] = b.hy; f[5] = b.hz;
+}
+
+// One warp's 128 leaves: faces -> leaf boxes -> heights 1..7, all stored. FULL = every leaf of the chunk exists
+// (compile-time true folds every bounds predicate away; the partial last chunk takes the generic instantiation).
+// Returns the warp root (height 7) in lane 0.
+template <bool BUILD, bool FULL>
+__device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, const uint32_t* __restrict__ perm,
+                                         uint32_t* __restrict__ faces_sorted, const float4* __restrict__ pos4,
+                                         float2* __restrict__ nodes, uint32_t T, uint32_t L, const LevelTable& lv,
+                                         float2* wsm, uint32_t warp_leaf0, uint32_t lane)
+{
     const uint32_t leaf0 = warp_leaf0 + lane * kLeavesPerThread;
-    float2* wsm = sm + 3 * (warp * kWarpLeaves); // this warp's 128-node staging area
-
+    auto in = [&](uint32_t i) { return FULL || i < T; };
     // ---- faces of this thread's 4 consecutive leaves ----
     uint32_t idx[12];
-    const bool full = leaf0 + 4 <= T;
+    const bool full = FULL || leaf0 + 4 <= T;
     if (BUILD)
     {
         uint32_t id[4];
@@ -473,12 +517,12 @@ __global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
         else
         {
 #pragma unroll
-            for (int k = 0; k < 4; k++) id[k] = (leaf0 + k < T) ? perm[leaf0 + k] : 0u;
+            for (int k = 0; k < 4; k++) id[k] = in(leaf0 + k) ? perm[leaf0 + k] : 0u;
         }
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-            const uint4 f = (leaf0 + k < T) ? __ldg(faces_in4 + id[k]) : make_uint4(0, 0, 0, 0);
+            const uint4 f = in(leaf0 + k) ? __ldg(faces_in4 + id[k]) : make_uint4(0, 0, 0, 0);
             idx[3 * k] = f.x; idx[3 * k + 1] = f.y; idx[3 * k + 2] = f.z;
         }
         if (full)
@@ -492,7 +536,7 @@ __global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
         {
 #pragma unroll
             for (int k = 0; k < 12; k++)
-                if (leaf0 + k / 3 < T) faces_sorted[3ull * leaf0 + k] = idx[k];
+                if (in(leaf0 + k / 3)) faces_sorted[3ull * leaf0 + k] = idx[k];
         }
     }
     else
@@ -508,7 +552,7 @@ __global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
         else
         {
 #pragma unroll
-            for (int k = 0; k < 12; k++) idx[k] = (leaf0 + k / 3 < T) ? faces_sorted[3ull * leaf0 + k] : 0u;
+            for (int k = 0; k < 12; k++) idx[k] = in(leaf0 + k / 3) ? faces_sorted[3ull * leaf0 + k] : 0u;
         }
     }
 
@@ -518,40 +562,111 @@ __global__ void __launch_bounds__(kEmitThreads, OIBVH_EMIT_MINB)
     for (int k = 0; k < 12; k++) v[k] = __ldg(pos4 + idx[k]); // idx = 0 for missing leaves: harmless load
     Box leaf[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 4; k++) leaf[k] = box_of(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+    Box h1a, h1b, cur;
+    if (FULL)
     {
-        leaf[k] = box_of(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
-        if (leaf0 + k < T) stage_box(wsm, lane * 4 + k, leaf[k]);
+        // Heights 0..2 (87.5 % of the bytes): staged with 128-bit shared stores in three per-warp areas and sent
+        // to global memory by TMA bulk copies (one elected lane, no per-lane copy loop). Level slices come from
+        // the host-built table; a slice is 8- or 16-byte aligned depending on the parity of its first node.
+        float2* st0 = wsm;                                   // 128 leaves   3072 B (+16)
+        float2* st1 = wsm + (3072 + 16) / 8;                 //  64 nodes    1536 B (+16)
+        float2* st2 = wsm + (3072 + 16 + 1536 + 16) / 8;     //  32 nodes     768 B (+16)
+        float2* g0 = nodes + 3ull * (lv.off[L] + warp_leaf0);
+        float2* g1 = nodes + 3ull * (lv.off[L - 1] + (warp_leaf0 >> 1));
+        float2* g2 = nodes + 3ull * (lv.off[L - 2] + (warp_leaf0 >> 2));
+        const uint32_t m0 = lv.off[L] & 1u, m1 = lv.off[L - 1] & 1u, m2 = lv.off[L - 2] & 1u;
+        float f[24];
+#pragma unroll
+        for (int k = 0; k < 4; k++) box_floats(leaf[k], f + 6 * k);
+        stage_floats<24>(st0 + lane * 12, f, m0);
+        h1a = box_merge(leaf[0], leaf[1]);
+        h1b = box_merge(leaf[2], leaf[3]);
+        float g[12];
+        box_floats(h1a, g);
+        box_floats(h1b, g + 6);
+        stage_floats<12>(st1 + lane * 6, g, m1);
+        cur = box_merge(h1a, h1b);
+        st2[m2 + lane * 3] = make_float2(cur.lx, cur.ly);
+        st2[m2 + lane * 3 + 1] = make_float2(cur.lz, cur.hx);
+        st2[m2 + lane * 3 + 2] = make_float2(cur.hy, cur.hz);
+        fence_proxy_async_smem(); // generic-proxy writes above -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0)
+        {
+            slice_store(g0, st0, 3072, m0);
+            slice_store(g1, st1, 1536, m1);
+            slice_store(g2, st2, 768, m2);
+            bulk_commit();
+        }
     }
-    // Level slices come from the host-built table (lv.off / lv.cnt by level), not from 64-bit arithmetic here.
-    // Heights 0..2 (87.5 % of the bytes) go through the warp staging area and leave as 128-bit coalesced stores;
-    // the few nodes of heights 3..7 are stored directly by the lane that owns them.
-    const uint32_t warp_valid = (warp_leaf0 < T) ? min((uint32_t)kWarpLeaves, T - warp_leaf0) : 0u;
-    __syncwarp();
-    if (warp_valid) warp_copy_out(nodes + 3ull * (lv.off[L] + warp_leaf0), wsm, 3 * warp_valid, lane);
-    __syncwarp();
-
-    Box h1a = (leaf0 + 1 < T) ? box_merge(leaf[0], leaf[1]) : leaf[0];
-    Box h1b = (leaf0 + 3 < T) ? box_merge(leaf[2], leaf[3]) : leaf[2];
-    if (leaf0 < T) stage_box(wsm, lane * 2, h1a);              // height 1: slots [0, 64)
-    if (leaf0 + 2 < T) stage_box(wsm, lane * 2 + 1, h1b);
-    Box cur = (leaf0 + 2 < T) ? box_merge(h1a, h1b) : h1a;
-    if (leaf0 < T) stage_box(wsm, 64 + lane, cur);              // height 2: slots [64, 96)
-    __syncwarp();
-    if (L >= 1 && warp_valid)
-        warp_copy_out(nodes + 3ull * (lv.off[L - 1] + (warp_leaf0 >> 1)), wsm, 3 * ((warp_valid + 1) >> 1), lane);
-    if (L >= 2 && warp_valid)
-        warp_copy_out(nodes + 3ull * (lv.off[L - 2] + (warp_leaf0 >> 2)), wsm + 3 * 64, 3 * ((warp_valid + 3) >> 2), lane);
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (in(leaf0 + k)) stage_box(wsm, lane * 4 + k, leaf[k]);
+        const uint32_t warp_valid = (warp_leaf0 < T) ? min((uint32_t)kWarpLeaves, T - warp_leaf0) : 0u;
+        __syncwarp();
+        if (warp_valid) warp_copy_out(nodes + 3ull * (lv.off[L] + warp_leaf0), wsm, 3 * warp_valid, lane);
+        __syncwarp();
+        h1a = in(leaf0 + 1) ? box_merge(leaf[0], leaf[1]) : leaf[0];
+        h1b = in(leaf0 + 3) ? box_merge(leaf[2], leaf[3]) : leaf[2];
+        if (in(leaf0)) stage_box(wsm, lane * 2, h1a);     // height 1: slots [0, 64)
+        if (in(leaf0 + 2)) stage_box(wsm, lane * 2 + 1, h1b);
+        cur = in(leaf0 + 2) ? box_merge(h1a, h1b) : h1a;
+        if (in(leaf0)) stage_box(wsm, 64 + lane, cur);    // height 2: slots [64, 96)
+        __syncwarp();
+        if (L >= 1 && warp_valid)
+            warp_copy_out(nodes + 3ull * (lv.off[L - 1] + (warp_leaf0 >> 1)), wsm, 3 * ((warp_valid + 1) >> 1), lane);
+        if (L >= 2 && warp_valid)
+            warp_copy_out(nodes + 3ull * (lv.off[L - 2] + (warp_leaf0 >> 2)), wsm + 3 * 64, 3 * ((warp_valid + 3) >> 2),
+                          lane);
+    }
 #pragma unroll
     for (int h = 3; h <= kWarpLevels; h++)
     {
         const int delta = 1 << (h - 3);
         const Box right = shfl_down_box(cur, delta);
         // right child = height h-1 node owned by lane + delta, first leaf = leaf0 + delta * 4
-        if (leaf0 + (uint32_t)delta * 4 < T) cur = box_merge(cur, right);
-        if ((lane & (2 * delta - 1)) == 0 && leaf0 < T && (uint32_t)h <= L)
+        if (in(leaf0 + (uint32_t)delta * 4)) cur = box_merge(cur, right);
+        if ((lane & (2 * delta - 1)) == 0 && in(leaf0) && (FULL || (uint32_t)h <= L))
             store_box(nodes, lv.off[L - h] + (leaf0 >> h), cur);
     }
+    if (FULL && lane == 0) bulk_wait_read(); // the staging areas may be reused / released after this
+    return cur;
+}
+
+#ifndef OIBVH_EMIT_MINB
+#define OIBVH_EMIT_MINB 4
+#endif
+#ifndef OIBVH_EMIT_MINB_BUILD
+#define OIBVH_EMIT_MINB_BUILD 3
+#endif
+// measured on B200: refit is fastest at 64 registers (4 CTAs/SM, no spills), build (one more gather level in
+// flight) at 85 registers (3 CTAs/SM); 48 registers / 5 CTAs spills and loses 15-25 %
+template <bool BUILD>
+__global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : OIBVH_EMIT_MINB)
+    tree_emit_kernel(const uint4* __restrict__ faces_in4,     // BUILD: input-order faces (16-byte records)
+                     const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
+                     uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
+                     const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
+                     const LevelTable lv, uint32_t* done_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    __shared__ float2 s_top[3 * 16]; // heights 7..10 of the chunk: 8 + 4 + 2 + 1 nodes
+
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t warp_leaf0 = chunk * kChunk + warp * kWarpLeaves;
+    const uint32_t leaf0 = warp_leaf0 + lane * kLeavesPerThread;
+    float2* wsm = sm + warp * (kWarpStageBytes / 8); // this warp's staging areas
+
+    Box cur;
+    if ((chunk + 1) * (uint32_t)kChunk <= T)
+        cur = emit_warp<BUILD, true>(faces_in4, perm, faces_sorted, pos4, nodes, T, L, lv, wsm, warp_leaf0, lane);
+    else
+        cur = emit_warp<BUILD, false>(faces_in4, perm, faces_sorted, pos4, nodes, T, L, lv, wsm, warp_leaf0, lane);
     if (lane == 0 && warp_leaf0 < T) stage_box(s_top, warp, cur); // warp root = height 7
     __syncthreads();
 
