@@ -28,7 +28,10 @@ METRIC = "ms/frame (build+refit+broad+narrow) at 1M tris"
 UNIT = "ms/frame"
 NU, NV = 1024, 512            # blob(1024, 512) -> 2^20 faces, 525 312 vertices
 OFFSET_B = (1.55, 0.1, 0.05)  # surfaces intersect along a closed curve
-ENTRY_LEVEL, EXPAND_LEVELS = 4, 3  # the reference's call: detectCollision(GPU0, 4, 3)  (main.cpp:284)
+# The reference calls detectCollision(GPU0, 4, 3) (main.cpp:284). Both values are traversal hints -- the pair set
+# does not depend on them -- so the bench keeps entry level 4 and lets the kernel pick the
+# levels per round from the front size (expand_levels = 0).
+ENTRY_LEVEL, EXPAND_LEVELS = 4, 0
 
 
 def workload_config(args, T, V):
@@ -43,10 +46,11 @@ def workload_config(args, T, V):
     }
 
 
-def make_meshes(nu=NU, nv=NV):
+def make_meshes(nu=NU, nv=NV, shuffle=True):
     from oibvh_b200 import meshgen
     pos, faces = meshgen.blob(nu, nv, seed=1234)
-    faces = meshgen.shuffle_faces(faces, seed=7)  # asset order is arbitrary: make the sort do real work
+    if shuffle:
+        faces = meshgen.shuffle_faces(faces, seed=7)  # asset order is arbitrary: make the sort do real work
     return pos, faces
 
 
@@ -147,7 +151,10 @@ def run_reference_arm(args):
         # largest size at which the unmodified reference is well-defined: SimpleCollide::detect keeps a depth
         # histogram `int a[19]` (src/cpu/simpleCollide.cpp:63-68), overrun for trees deeper than 18 = 2^18 faces
         nu, nv = 512, 256
-        pos, faces = make_meshes(nu, nv)
+        # generator (file-like, spatially coherent) face order: SimpleBVH splits faces in INPUT order without any
+        # spatial sort (src/cpu/simpleBVH.cpp:122-159), so on the shuffled order the GPU arm gets, its boxes span
+        # the whole mesh and detect() degenerates to O(n^2) (90 s at 65 K faces). The pair SET is order-independent.
+        pos, faces = make_meshes(nu, nv, shuffle=False)
         T = len(faces)
         R = oracle.Ref()
         mA, mB = R.mesh_create(pos, faces), R.mesh_create(pos, faces)
@@ -177,7 +184,7 @@ def run_reference_arm(args):
         raw = float(np.mean(times))
         value = raw * scale
         kind, sample = "reference", (f"unmodified reference CPU classes on 2 x {T} tris (largest size where "
-                                     f"SimpleCollide's int a[19] depth histogram is in bounds), {steps} frames; "
+                                     f"SimpleCollide's int a[19] depth histogram is in bounds), faces in generator order, {steps} frames; "
                                      f"ms/frame scaled x{scale:.1f} by triangle count to 2 x {T_full}")
         extra = {"raw_ms_per_sample_frame": raw, "pairs_in_sample": n_pairs, "steps_run": steps}
     else:
@@ -321,7 +328,13 @@ def run_gpu_arm(args):
             stage[k] += ms[k]
     ctx.enable_timing(False)
     stage = {k: v / args.steps for k, v in stage.items()}
-    rounds = scene.round_stats()
+    rounds = [r for r in scene.round_stats() if r]
+    # broad and narrow phase share one persistent kernel: split its time by the SM-cycle stamps of its phases
+    cyc = scene.phase_cycles()
+    if cyc and sum(cyc) > 0:
+        share = cyc[-1] / float(sum(cyc))
+        both = stage["broad"] + stage["narrow"]
+        stage["narrow"], stage["broad"] = both * share, both * (1.0 - share)
 
     # ---- timed region 3: end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside ----
     n_e2e = args.steps
@@ -393,7 +406,7 @@ def run_gpu_arm(args):
             "config": workload_config(args, T, V),
             "frame_mtris_per_s": 2 * T / (ms_per_step * 1e-3) / 1e6,
             "build_mtris_per_s": T / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None,
-            "stage_ms": stage, "pairs": n_pairs if dist is None else int(ctr_all[:, 1].sum().item()),
+            "stage_ms": stage, "collide_phase_cycles": cyc, "pairs": n_pairs if dist is None else int(ctr_all[:, 1].sum().item()),
             "pairs_this_rank": n_pairs, "candidates": n_cand, "bvtt_rounds": rounds,
             "gpu_launches": int(l1 - l0),
             "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,

@@ -1,0 +1,391 @@
+// C++ facade of oibvh_b200: the reference's host operator surface on top of the C ABI (include/oibvh_b200.h).
+//
+// Same class / method / member names as the reference so that its driver code (src/main.cpp:127-151 set-up,
+// :208-319 per-frame loop, minus the GL/ImGui calls) compiles against this header:
+//
+//   aabb_box_t, tri_pair_node_t, int_tri_pair_node_t      include/utils/utils.h:13-61
+//   Vertex, Mesh{translate, rotate*, transform, m_vertices, m_indices, m_aabb, ...}   include/utils/mesh.h:20-187
+//   OibvhTree{OibvhTree(mesh), OibvhTree(other, mesh), build, refit, getDepth, getPrimCount}   include/cuda/oibvhTree.cuh:44-93
+//   DeviceType, Scene{addOibvhTree, detectCollision, getIntTriPairCount}              include/cuda/scene.cuh:12-67
+//
+// Differences, all deliberate:
+//   * no OpenGL: draw()/VAO/VBO members are gone (rendering is out of scope);
+//   * trees live on the device; m_aabbTree / m_faces / m_positions are refreshed from the device by syncHost()
+//     (the reference copies them back after every build/refit, oibvhTree.cu:232, 375-377) -- call it when you read them;
+//   * failures throw std::runtime_error carrying oibvh_last_error() (the reference checks nothing);
+//   * vector/matrix types: define OIBVH_FACADE_USE_GLM before including to use glm::vec3/mat4 (drop-in inside the
+//     reference tree); otherwise the minimal oibvh::vec types below, which follow glm's arithmetic order exactly.
+// Header-only; link with -loibvh_b200.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../oibvh_b200.h"
+
+#ifdef OIBVH_FACADE_USE_GLM
+#include <glm/glm.hpp>
+#include <glm/gtc/matrix_transform.hpp>
+namespace oibvh_math = glm;
+#else
+namespace oibvh_math
+{
+struct vec2
+{
+    float x = 0, y = 0;
+};
+struct vec3
+{
+    float x = 0, y = 0, z = 0;
+    vec3() = default;
+    explicit vec3(float s) : x(s), y(s), z(s) {}
+    vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+struct uvec3
+{
+    unsigned int x = 0, y = 0, z = 0;
+};
+struct vec4
+{
+    float x = 0, y = 0, z = 0, w = 0;
+};
+// column-major 4x4 like glm::mat4: c[j] is column j
+struct mat4
+{
+    vec4 c[4];
+    vec4& operator[](int j) { return c[j]; }
+    const vec4& operator[](int j) const { return c[j]; }
+};
+inline vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
+inline vec4 operator*(const vec4& a, float s) { return vec4{a.x * s, a.y * s, a.z * s, a.w * s}; }
+inline vec4 operator+(const vec4& a, const vec4& b) { return vec4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+inline vec3 min(const vec3& x, const vec3& y) // glm::min(x, y) = (y < x) ? y : x per component
+{
+    return vec3(y.x < x.x ? y.x : x.x, y.y < x.y ? y.y : x.y, y.z < x.z ? y.z : x.z);
+}
+inline vec3 max(const vec3& x, const vec3& y) // glm::max(x, y) = (x < y) ? y : x
+{
+    return vec3(x.x < y.x ? y.x : x.x, x.y < y.y ? y.y : x.y, x.z < y.z ? y.z : x.z);
+}
+inline mat4 identity()
+{
+    mat4 m;
+    m[0].x = m[1].y = m[2].z = m[3].w = 1.0f;
+    return m;
+}
+inline float radians(float deg) { return deg * static_cast<float>(0.01745329251994329576923690768489); }
+// glm::translate (third/glm/ext/matrix_transform.inl:10-15)
+inline mat4 translate(const mat4& m, const vec3& v)
+{
+    mat4 r = m;
+    r[3] = m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3];
+    return r;
+}
+// glm::rotate (third/glm/ext/matrix_transform.inl:18-46)
+inline mat4 rotate(const mat4& m, float angle, const vec3& v)
+{
+    const float c = std::cos(angle), s = std::sin(angle);
+    const float inv = 1.0f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    const vec3 axis(v.x * inv, v.y * inv, v.z * inv);
+    const vec3 temp((1.0f - c) * axis.x, (1.0f - c) * axis.y, (1.0f - c) * axis.z);
+    float R[3][3];
+    R[0][0] = c + temp[0] * axis[0];
+    R[0][1] = temp[0] * axis[1] + s * axis[2];
+    R[0][2] = temp[0] * axis[2] - s * axis[1];
+    R[1][0] = temp[1] * axis[0] - s * axis[2];
+    R[1][1] = c + temp[1] * axis[1];
+    R[1][2] = temp[1] * axis[2] + s * axis[0];
+    R[2][0] = temp[2] * axis[0] + s * axis[1];
+    R[2][1] = temp[2] * axis[1] - s * axis[0];
+    R[2][2] = c + temp[2] * axis[2];
+    mat4 r;
+    r[0] = m[0] * R[0][0] + m[1] * R[0][1] + m[2] * R[0][2];
+    r[1] = m[0] * R[1][0] + m[1] * R[1][1] + m[2] * R[1][2];
+    r[2] = m[0] * R[2][0] + m[1] * R[2][1] + m[2] * R[2][2];
+    r[3] = m[3];
+    return r;
+}
+// glm mat4 * vec4 (third/glm/detail/type_mat4x4.inl:561-572): (m0*x + m1*y) + (m2*z + m3*w)
+inline vec4 operator*(const mat4& m, const vec4& v) { return (m[0] * v.x + m[1] * v.y) + (m[2] * v.z + m[3] * v.w); }
+} // namespace oibvh_math
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// plain records (include/utils/utils.h:13-61)
+// ---------------------------------------------------------------------------------------------------------
+typedef struct aabb_box
+{
+    oibvh_math::vec3 m_minimum{std::numeric_limits<float>::max()};
+    oibvh_math::vec3 m_maximum{-std::numeric_limits<float>::max()};
+    void merge(const aabb_box& o)
+    {
+        m_minimum = oibvh_math::min(m_minimum, o.m_minimum);
+        m_maximum = oibvh_math::max(m_maximum, o.m_maximum);
+    }
+    bool overlap(const aabb_box& o) const
+    {
+        return (m_minimum.x <= o.m_maximum.x && m_maximum.x >= o.m_minimum.x) &&
+               (m_minimum.y <= o.m_maximum.y && m_maximum.y >= o.m_minimum.y) &&
+               (m_minimum.z <= o.m_maximum.z && m_maximum.z >= o.m_minimum.z);
+    }
+} aabb_box_t;
+static_assert(sizeof(aabb_box_t) == sizeof(oibvh_aabb), "aabb_box_t must stay 24 bytes");
+
+typedef struct tri_pair_node
+{
+    unsigned int m_triIndex[2];
+} tri_pair_node_t;
+
+typedef struct int_tri_pair_node
+{
+    unsigned int m_bvhIndex[2];
+    unsigned int m_triIndex[2];
+} int_tri_pair_node_t;
+static_assert(sizeof(int_tri_pair_node_t) == sizeof(oibvh_int_tri_pair), "int_tri_pair_node_t must stay 16 bytes");
+
+namespace oibvh_detail
+{
+inline void check(int rc)
+{
+    if (rc != OIBVH_OK) throw std::runtime_error(std::string("oibvh_b200: ") + oibvh_last_error());
+}
+// one context per device, created on first use (the reference uses the current device + default stream)
+inline oibvh_ctx* context(int device = 0)
+{
+    static oibvh_ctx* ctx[16] = {nullptr};
+    if (device < 0 || device >= 16) throw std::runtime_error("oibvh_b200: bad device index");
+    if (!ctx[device]) check(oibvh_ctx_create(device, &ctx[device]));
+    return ctx[device];
+}
+} // namespace oibvh_detail
+
+// ---------------------------------------------------------------------------------------------------------
+// Mesh (include/utils/mesh.h) -- geometry and transforms only
+// ---------------------------------------------------------------------------------------------------------
+struct Vertex
+{
+    oibvh_math::vec3 m_position;
+    oibvh_math::vec3 m_normal;
+    oibvh_math::vec2 m_texCoords;
+};
+
+class Mesh
+{
+public:
+    Mesh() = delete;
+    Mesh(const std::vector<Vertex>& vertices, const std::vector<unsigned int>& indices)
+        : m_verticesCount((unsigned)vertices.size())
+        , m_facesCount((unsigned)(indices.size() / 3))
+        , m_vertices(vertices)
+        , m_indices(indices)
+    {
+        // Mesh::setupAABB (src/utils/mesh.cpp:91-98): note the argument order
+        for (const auto& v : m_vertices)
+        {
+            m_aabb.m_maximum = oibvh_math::max(v.m_position, m_aabb.m_maximum);
+            m_aabb.m_minimum = oibvh_math::min(v.m_position, m_aabb.m_minimum);
+        }
+        // Mesh::setupCenter (:145-153)
+        m_center = oibvh_math::vec3(0.0f);
+        for (const auto& v : m_vertices)
+        {
+            m_center.x += v.m_position.x;
+            m_center.y += v.m_position.y;
+            m_center.z += v.m_position.z;
+        }
+        const float n = (float)m_verticesCount;
+        m_center.x /= n;
+        m_center.y /= n;
+        m_center.z /= n;
+    }
+    Mesh(const Mesh&) = default;
+
+    void rotateX(const float angle = 1.0f) { rotate(oibvh_math::vec3(1.0f, 0.0f, 0.0f), angle); }
+    void rotateY(const float angle = 1.0f) { rotate(oibvh_math::vec3(0.0f, 1.0f, 0.0f), angle); }
+    void rotateZ(const float angle = 1.0f) { rotate(oibvh_math::vec3(0.0f, 0.0f, 1.0f), angle); }
+    // Mesh::rotate (mesh.cpp:171-178): about the mesh centre, angle in degrees
+    void rotate(const oibvh_math::vec3 axis, const float angle)
+    {
+        oibvh_math::mat4 m = oibvh_math::identity();
+        m = oibvh_math::translate(m, m_center);
+        m = oibvh_math::rotate(m, oibvh_math::radians(angle), axis);
+        m = oibvh_math::translate(m, -m_center);
+        transform(m);
+    }
+    void translate(const oibvh_math::vec3 t) { transform(oibvh_math::translate(oibvh_math::identity(), t)); }
+    // Mesh::transform (mesh.cpp:187-213). The reference round-trips every vertex through a GPU kernel; the values
+    // are the same glm expression evaluated here on the host.
+    void transform(const oibvh_math::mat4 M)
+    {
+        const oibvh_math::vec4 c = M * oibvh_math::vec4{m_center.x, m_center.y, m_center.z, 1.0f};
+        m_center = oibvh_math::vec3(c.x, c.y, c.z);
+        for (auto& v : m_vertices)
+        {
+            const oibvh_math::vec4 p = M * oibvh_math::vec4{v.m_position.x, v.m_position.y, v.m_position.z, 1.0f};
+            v.m_position = oibvh_math::vec3(p.x, p.y, p.z);
+        }
+    }
+
+    unsigned int m_verticesCount;
+    unsigned int m_facesCount;
+    std::vector<Vertex> m_vertices;
+    std::vector<unsigned int> m_indices;
+    aabb_box_t m_aabb;
+    oibvh_math::vec3 m_center;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// OibvhTree (include/cuda/oibvhTree.cuh:44-93)
+// ---------------------------------------------------------------------------------------------------------
+class Scene;
+class OibvhTree
+{
+public:
+    OibvhTree() = delete;
+    OibvhTree(const OibvhTree&) = delete;
+    OibvhTree& operator=(const OibvhTree&) = delete;
+
+    explicit OibvhTree(const std::shared_ptr<Mesh> mesh) : m_mesh(mesh), m_buildDone(false)
+    {
+        std::vector<float> pos = packedPositions();
+        const float aabb[6] = {mesh->m_aabb.m_minimum.x, mesh->m_aabb.m_minimum.y, mesh->m_aabb.m_minimum.z,
+                               mesh->m_aabb.m_maximum.x, mesh->m_aabb.m_maximum.y, mesh->m_aabb.m_maximum.z};
+        oibvh_detail::check(oibvh_tree_create(oibvh_detail::context(), pos.data(), mesh->m_verticesCount,
+                                              mesh->m_indices.data(), mesh->m_facesCount, aabb, &m_handle));
+    }
+    // copy constructor of the reference (src/cuda/oibvhTree.cu:17-33): same Morton order / tree as `other`
+    OibvhTree(const std::shared_ptr<OibvhTree> other, const std::shared_ptr<Mesh> mesh)
+        : m_mesh(mesh), m_buildDone(other->m_buildDone)
+    {
+        oibvh_detail::check(oibvh_tree_clone(other->m_handle, &m_handle));
+    }
+    ~OibvhTree() { oibvh_tree_destroy(m_handle); }
+
+    void build()
+    {
+        oibvh_detail::check(oibvh_tree_build(m_handle));
+        m_buildDone = true;
+    }
+    // re-reads the mesh positions like the reference (oibvhTree.cu:196-199)
+    void refit()
+    {
+        std::vector<float> pos = packedPositions();
+        oibvh_detail::check(oibvh_tree_set_positions(m_handle, pos.data()));
+        oibvh_detail::check(oibvh_tree_refit(m_handle));
+        oibvh_detail::check(oibvh_ctx_synchronize(oibvh_detail::context())); // `pos` is about to go away
+    }
+    unsigned int getDepth() const
+    {
+        uint32_t d = 0;
+        oibvh_detail::check(oibvh_tree_get_info(m_handle, nullptr, nullptr, nullptr, &d));
+        return d;
+    }
+    unsigned int getPrimCount() const
+    {
+        uint32_t t = 0;
+        oibvh_detail::check(oibvh_tree_get_info(m_handle, &t, nullptr, nullptr, nullptr));
+        return t;
+    }
+    // refresh m_aabbTree / m_faces / m_positions (and the sorted->input face permutation) from the device
+    void syncHost()
+    {
+        uint32_t T = 0, V = 0, N = 0;
+        oibvh_detail::check(oibvh_tree_get_info(m_handle, &T, &V, &N, nullptr));
+        m_aabbTree.resize(N);
+        m_faces.resize(T);
+        m_perm.resize(T);
+        static_assert(sizeof(oibvh_math::uvec3) == 12, "uvec3 is three packed uint32");
+        oibvh_detail::check(oibvh_tree_download(m_handle, reinterpret_cast<oibvh_aabb*>(m_aabbTree.data()),
+                                                reinterpret_cast<uint32_t*>(m_faces.data()), m_perm.data()));
+        std::vector<float> p(3 * (size_t)V);
+        oibvh_detail::check(oibvh_tree_download_positions(m_handle, p.data()));
+        m_positions.resize(V);
+        for (uint32_t i = 0; i < V; i++) m_positions[i] = oibvh_math::vec3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    }
+    oibvh_tree* handle() const { return m_handle; }
+
+    std::vector<aabb_box_t> m_aabbTree;          // N nodes, real-index order (after syncHost)
+    std::vector<oibvh_math::uvec3> m_faces;      // Morton-sorted faces (after syncHost)
+    std::vector<oibvh_math::vec3> m_positions;   // (after syncHost)
+    std::vector<uint32_t> m_perm;                // sorted position -> input face id (extension)
+    bool m_buildDone;
+
+private:
+    std::vector<float> packedPositions() const
+    {
+        std::vector<float> pos(3 * (size_t)m_mesh->m_verticesCount);
+        for (unsigned i = 0; i < m_mesh->m_verticesCount; i++)
+        {
+            pos[3 * i] = m_mesh->m_vertices[i].m_position.x;
+            pos[3 * i + 1] = m_mesh->m_vertices[i].m_position.y;
+            pos[3 * i + 2] = m_mesh->m_vertices[i].m_position.z;
+        }
+        return pos;
+    }
+    std::shared_ptr<Mesh> m_mesh;
+    oibvh_tree* m_handle = nullptr;
+    friend class Scene;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Scene (include/cuda/scene.cuh:12-67)
+// ---------------------------------------------------------------------------------------------------------
+enum class DeviceType
+{
+    CPU = -1,
+    GPU0,
+    GPU1,
+    GPU2,
+    GPU3,
+    GPU4,
+    GPU5,
+    GPU6,
+    GPU7,
+    GPU8
+};
+
+class Scene
+{
+public:
+    Scene() { oibvh_detail::check(oibvh_scene_create(oibvh_detail::context(), &m_handle)); }
+    Scene(const Scene&) = delete;
+    Scene& operator=(const Scene&) = delete;
+    ~Scene() { oibvh_scene_destroy(m_handle); }
+
+    void addOibvhTree(std::shared_ptr<OibvhTree> oibvhTree)
+    {
+        oibvh_detail::check(oibvh_scene_add_tree(m_handle, oibvhTree->m_handle));
+        m_oibvhTrees.push_back(oibvhTree);
+    }
+    // Scene::detectCollision (src/cuda/scene.cu:157-185). DeviceType::CPU is an empty TODO in the reference
+    // (scene.cu:187-190); there is no CPU path here, so it throws.
+    void detectCollision(const DeviceType deviceType = DeviceType::GPU0, const unsigned int entryLevel = 0,
+                         const unsigned int expandLevels = 1)
+    {
+        if (deviceType != DeviceType::GPU0)
+            throw std::runtime_error("oibvh_b200: this Scene lives on GPU0 (DeviceType::CPU is a TODO in the reference)");
+        uint32_t n = 0, c = 0;
+        oibvh_detail::check(oibvh_scene_detect(m_handle, entryLevel, expandLevels, &n, &c));
+        m_intTriPairCount = n;
+        m_candidateCount = c;
+        m_intTriPairs.resize(n);
+        oibvh_detail::check(oibvh_scene_get_pairs(m_handle, reinterpret_cast<oibvh_int_tri_pair*>(m_intTriPairs.data())));
+    }
+    unsigned int getIntTriPairCount() const { return m_intTriPairCount; }
+    unsigned int getCandidateCount() const { return m_candidateCount; } // extension
+
+    std::vector<int_tri_pair_node_t> m_intTriPairs; // {bvhA < bvhB, triA, triB}; tri = Morton-sorted position
+
+private:
+    std::vector<std::shared_ptr<OibvhTree>> m_oibvhTrees;
+    oibvh_scene* m_handle = nullptr;
+    unsigned int m_intTriPairCount = 0;
+    unsigned int m_candidateCount = 0;
+};

@@ -830,12 +830,14 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     const uint32_t n_obj = (uint32_t)s->trees.size();
     uint32_t maxL = 0;
     for (auto* t : s->trees) maxL = std::max(maxL, t->L);
-    if (expand_levels == 0) expand_levels = 3u;
-    expand_levels = std::min(expand_levels, 4u);  // one warp tests the 4^k descendant pairs of a node pair
+    // expand_levels == 0: the kernel picks 2..4 levels per round from the front size; `rounds` is then only an upper
+    // bound (the kernel stops as soon as a front is empty). One warp tests the 4^k descendant pairs of a node pair.
+    expand_levels = std::min(expand_levels, 4u);
     // round 0 descends from the roots to the entry level (a hint: the pair set does not depend on it)
-    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 5u) : expand_levels;
+    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 5u) : (expand_levels ? expand_levels : 4u);
     const uint32_t reached = std::min(k0, maxL);
-    const uint32_t rounds = 1 + (maxL - reached + expand_levels - 1) / expand_levels; // leaf pairs leave as candidates
+    const uint32_t kmin = expand_levels ? expand_levels : 2u;
+    const uint32_t rounds = 1 + (maxL - reached + kmin - 1) / kmin; // leaf pairs leave as candidates
     if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
 
     CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));

@@ -107,12 +107,38 @@ __device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters
 // ---------------------------------------------------------------------------------------------------
 constexpr int kStageCap = 256; // records per warp staging buffer (4 KB)
 
-__device__ void expand_phase(uint4* s_stage, const ObjDesc* __restrict__ objs, const uint4* in, uint4* out,
-                             uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint32_t* counters, uint32_t round,
-                             uint32_t front_size, uint32_t levels, uint32_t rank, uint32_t world)
+constexpr int kObjCache = 64; // object descriptors + level tables kept in shared memory (more: L1/L2 + arithmetic)
+
+__device__ __forceinline__ ObjDesc get_obj(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, uint32_t i)
+{
+    return i < (uint32_t)kObjCache ? s_objs[i] : load_obj(objs, i);
+}
+
+// level geometry of an object: from the shared-memory tables for cached objects, from arithmetic otherwise
+struct LevelView
+{
+    const uint32_t* off; // null -> compute
+    const uint32_t* cnt;
+    uint32_t T, L;
+    __device__ __forceinline__ uint32_t offset(uint32_t l) const { return off ? off[l] : level_offset(T, L, l); }
+    __device__ __forceinline__ uint32_t count(uint32_t l) const { return cnt ? cnt[l] : level_count(T, L, l); }
+};
+__device__ __forceinline__ LevelView level_view(const uint32_t* s_lv, uint32_t obj, const ObjDesc& d)
+{
+    LevelView v;
+    v.T = d.T;
+    v.L = d.L;
+    v.off = obj < (uint32_t)kObjCache ? s_lv + obj * 64 : nullptr;
+    v.cnt = obj < (uint32_t)kObjCache ? s_lv + obj * 64 + 32 : nullptr;
+    return v;
+}
+
+__device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32_t* s_lv,
+                             const ObjDesc* __restrict__ objs, const uint4* in, uint4* out, uint32_t front_cap,
+                             uint4* cand, uint32_t cand_cap, uint32_t* counters, uint32_t round, uint32_t front_size,
+                             uint32_t levels, uint32_t rank, uint32_t world)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    // fronts are produced by other SMs inside this same launch: read them through L2 (ld.cg)
     const uint32_t n = min(front_size, front_cap);
     uint32_t* next_count = counters + CTR_FRONT0 + round + 1;
     const uint32_t total_warps = gridDim.x * kColWarps;
@@ -135,51 +161,79 @@ __device__ void expand_phase(uint4* s_stage, const ObjDesc* __restrict__ objs, c
         staged = 0;
     };
 
-    for (uint32_t p = blockIdx.x * kColWarps + warp; p < n; p += total_warps)
+    // A work item is one 64-combination group of one pair's descendant rectangle (4^levels combinations at most):
+    // a 3-level rectangle is one item, the seed round (4..5 levels) is spread over several warps. Each lane tests
+    // two combinations per item, so four box loads per lane are in flight together.
+    const uint32_t gshift = 2 * levels > 6 ? 2 * levels - 6 : 0; // log2(groups per pair)
+    const uint32_t items = n << gshift;                          // n < 2^26, gshift <= 4
+    uint32_t w = blockIdx.x * kColWarps + warp;
+    // fronts are produced by other SMs inside this same launch: read them through L2 (ld.cg); the entry of the
+    // NEXT item is fetched before the current one is processed (one round trip off the critical path)
+    uint4 it_next = make_uint4(0, 0, 0, 0);
+    if (w < items) it_next = __ldcg(in + (w >> gshift));
+    for (; w < items; w += total_warps)
     {
-        const uint4 it = __ldcg(in + p); // same address in every lane: one broadcast load
-        const ObjDesc A = load_obj(objs, it.x), B = load_obj(objs, it.y);
+        const uint4 it = it_next;
+        const uint32_t p = w >> gshift, group = w & ((1u << gshift) - 1);
+        if (w + total_warps < items) it_next = __ldcg(in + ((w + total_warps) >> gshift));
+        const ObjDesc A = get_obj(s_objs, objs, it.x), B = get_obj(s_objs, objs, it.y);
+        const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
         const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
         const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
         const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
         const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
-        if (round == 0)
-        {
-            // seeds are untested: prune object pairs whose root boxes are disjoint
-            const Box a = load_box(nodesA, level_offset(A.T, A.L, la) + pa);
-            const Box b = load_box(nodesB, level_offset(B.T, B.L, lb) + pb);
-            if (!box_overlap(a, b)) continue;
-        }
         const uint32_t da = min(levels, A.L - la), db = min(levels, B.L - lb);
         const uint32_t lca = la + da, lcb = lb + db;
         const uint32_t fa = pa << da, fb = pb << db;
-        const uint32_t nA = min(1u << da, level_count(A.T, A.L, lca) - fa);
-        const uint32_t nB = min(1u << db, level_count(B.T, B.L, lcb) - fb);
-        const uint32_t baseA = level_offset(A.T, A.L, lca) + fa, baseB = level_offset(B.T, B.L, lcb) + fb;
+        const uint32_t nA = min(1u << da, va.count(lca) - fa);
+        const uint32_t nB = min(1u << db, vb.count(lcb) - fb);
+        const uint32_t combos = nA * nB;
+        if (group * 64 >= combos) continue; // warp-uniform: clamped rectangle, nothing in this group
+        const uint32_t baseA = va.offset(lca) + fa, baseB = vb.offset(lcb) + fb;
+        const uint32_t c0 = group * 64 + lane, c1 = c0 + 32;
+        bool hit0 = c0 < combos, hit1 = c1 < combos;
+        // round 0: the seed rectangle is dealt round-robin to the shards
+        if (world > 1 && round == 0)
+        {
+            hit0 = hit0 && ((p + c0) % world) == rank;
+            hit1 = hit1 && ((p + c1) % world) == rank;
+        }
+        // nB is a power of two unless the rectangle is clamped by the end of the level
+        const uint32_t ia0 = c0 / nB, ib0 = c0 - ia0 * nB, ia1 = c1 / nB, ib1 = c1 - ia1 * nB;
+        Box a0, b0, a1, b1;
+        if (hit0)
+        {
+            a0 = load_box(nodesA, baseA + ia0);
+            b0 = load_box(nodesB, baseB + ib0);
+        }
+        if (hit1)
+        {
+            a1 = load_box(nodesA, baseA + ia1);
+            b1 = load_box(nodesB, baseB + ib1);
+        }
+        if (round == 0)
+        {
+            // seeds are untested: prune object pairs whose root boxes are disjoint (loads overlap the ones above)
+            const Box ra = load_box(nodesA, va.offset(la) + pa);
+            const Box rb = load_box(nodesB, vb.offset(lb) + pb);
+            if (!box_overlap(ra, rb)) continue; // warp-uniform
+        }
+        if (hit0) hit0 = box_overlap(a0, b0);
+        if (hit1) hit1 = box_overlap(a1, b1);
         const bool to_cand = (lca == A.L) && (lcb == B.L);
         if (staged && to_cand != staged_cand) flush();
         staged_cand = to_cand;
-        const uint32_t combos = nA * nB;
-        for (uint32_t c0 = 0; c0 < combos; c0 += 32)
-        {
-            const uint32_t c = c0 + lane;
-            bool hit = c < combos;
-            // round 0: the seed rectangle is dealt round-robin to the shards
-            if (world > 1 && round == 0 && hit) hit = ((p + c) % world) == rank;
-            const uint32_t ia = c / nB, ib = c - ia * nB;
-            if (hit) hit = box_overlap(load_box(nodesA, baseA + ia), load_box(nodesB, baseB + ib));
-            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            const uint32_t cnt = __popc(mask);
-            if (staged + cnt > (uint32_t)kStageCap) flush();
-            if (hit)
-            {
-                const uint32_t slot = staged + __popc(mask & lanemask_lt());
-                stage[slot] = to_cand ? make_uint4(it.x, it.y, fa + ia, fb + ib)
-                                      : make_uint4(it.x, it.y, (lca << kNodeLevelShift) | (fa + ia),
-                                                   (lcb << kNodeLevelShift) | (fb + ib));
-            }
-            staged += cnt;
-        }
+        const uint32_t mask0 = __ballot_sync(0xffffffffu, hit0), mask1 = __ballot_sync(0xffffffffu, hit1);
+        const uint32_t cnt0 = __popc(mask0), cnt = cnt0 + __popc(mask1);
+        if (staged + cnt > (uint32_t)kStageCap) flush();
+        const uint32_t na = lca << kNodeLevelShift, nb = lcb << kNodeLevelShift;
+        if (hit0)
+            stage[staged + __popc(mask0 & lanemask_lt())] =
+                to_cand ? make_uint4(it.x, it.y, fa + ia0, fb + ib0) : make_uint4(it.x, it.y, na | (fa + ia0), nb | (fb + ib0));
+        if (hit1)
+            stage[staged + cnt0 + __popc(mask1 & lanemask_lt())] =
+                to_cand ? make_uint4(it.x, it.y, fa + ia1, fb + ib1) : make_uint4(it.x, it.y, na | (fa + ia1), nb | (fb + ib1));
+        staged += cnt;
     }
     flush();
 }
@@ -266,7 +320,7 @@ __device__ __forceinline__ V3 load_v3(const float4* __restrict__ pos, uint32_t v
     return V3{p.x, p.y, p.z};
 }
 
-__device__ void narrow_phase(const ObjDesc* __restrict__ objs, const uint4* cand, uint32_t cand_cap,
+__device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, const uint4* cand, uint32_t cand_cap,
                              uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* counters, uint32_t n_cand)
 {
     const uint32_t lane = lane_id();
@@ -280,7 +334,7 @@ __device__ void narrow_phase(const ObjDesc* __restrict__ objs, const uint4* cand
         if (i < n)
         {
             c = __ldcg(cand + i);
-            const ObjDesc A = load_obj(objs, c.x), B = load_obj(objs, c.y);
+            const ObjDesc A = get_obj(s_objs, objs, c.x), B = get_obj(s_objs, objs, c.y);
             const uint32_t* fa = A.faces + 3ull * c.z;
             const uint32_t* fb = B.faces + 3ull * c.w;
             const V3 P1 = load_v3(A.pos, __ldg(fa)), P2 = load_v3(A.pos, __ldg(fa + 1)), P3 = load_v3(A.pos, __ldg(fa + 2));
@@ -315,6 +369,17 @@ __global__ void __launch_bounds__(kColThreads, 1)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_stage = reinterpret_cast<uint4*>(smem_raw); // kColWarps x kStageCap records
+    __shared__ __align__(16) ObjDesc s_objs[kObjCache];
+    __shared__ uint32_t s_lv[kObjCache * 64]; // per cached object: off[32], cnt[32]
+    for (uint32_t i = threadIdx.x; i < min(n_obj, (uint32_t)kObjCache) * 32; i += blockDim.x)
+    {
+        const uint32_t o = i >> 5, l = i & 31u;
+        const ObjDesc d = load_obj(objs, o);
+        if (l == 0) s_objs[o] = d;
+        s_lv[o * 64 + l] = l <= d.L ? level_offset(d.T, d.L, l) : 0u;
+        s_lv[o * 64 + 32 + l] = l <= d.L ? level_count(d.T, d.L, l) : 0u;
+    }
+    __syncthreads();
     uint32_t gen = 0;
     auto stamp = [&](uint32_t i) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && i < CTR_WORDS - CTR_TIME0) counters[CTR_TIME0 + i] = (uint32_t)clock64();
@@ -327,14 +392,19 @@ __global__ void __launch_bounds__(kColThreads, 1)
     {
         uint4* in = (r & 1) ? front1 : front0;
         uint4* out = (r & 1) ? front0 : front1;
-        expand_phase(s_stage, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size,
-                     r == 0 ? levels0 : levels, rank, world);
+        // levels == 0: adaptive. Small fronts are latency-bound (one barrier per round): descend 4 levels per
+        // round; large fronts are throughput-bound: fewer levels prune earlier and test far fewer box pairs.
+        // front_size is uniform over the grid, so every CTA picks the same value.
+        uint32_t k = r == 0 ? levels0 : levels;
+        if (k == 0) k = front_size < 4096u ? 4u : (front_size < 32768u ? 3u : 2u);
+        expand_phase(s_stage, s_objs, s_lv, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size, k, rank,
+                     world);
         front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0 + r + 1);
         stamp(gen);
     }
     const uint32_t n_cand = grid_barrier(counters, ++gen, counters + CTR_CANDIDATES);
     stamp(gen);
-    narrow_phase(objs, cand, cand_cap, pairs, pair_cap, counters, n_cand);
+    narrow_phase(s_objs, objs, cand, cand_cap, pairs, pair_cap, counters, n_cand);
     __syncthreads();
     stamp(gen + 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = gen + 2; // number of stamps

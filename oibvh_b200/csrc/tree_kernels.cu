@@ -659,7 +659,6 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint32_t chunk = blockIdx.x;
     const uint32_t warp_leaf0 = chunk * kChunk + warp * kWarpLeaves;
-    const uint32_t leaf0 = warp_leaf0 + lane * kLeavesPerThread;
     float2* wsm = sm + warp * (kWarpStageBytes / 8); // this warp's staging areas
 
     Box cur;
