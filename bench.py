@@ -397,6 +397,13 @@ def run_gpu_arm(args):
         build_bytes = 112 * T + 24 * V + 24 * N
         refit_ms = stage["refit"] / 2.0                        # two refit launches per frame
         build_ms = stage["build"] / 2.0
+        traffic = None
+        try:  # DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("T") == T:
+                traffic = int(tr["dram_bytes_read_per_launch"]) + int(tr["dram_bytes_write_per_launch"])
+        except Exception:
+            pass
         refit_gbs = refit_bytes / (refit_ms * 1e-3) / 1e9 if refit_ms > 0 else 0.0
         build_gbs = build_bytes / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0
         line = {
@@ -414,10 +421,10 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": {"bound": "hbm", "kernel": "tree_emit_kernel<false> (refit: leaf AABBs + whole bottom-up "
                          "reduction, one launch per mesh)", "achieved": refit_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": refit_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": refit_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": refit_bytes, "ms_per_launch": refit_ms,
                          "timing": "CUDA events around the launch, eager second pass over the same K frames"},
-            "roofline_build": {"bound": "hbm", "stage": "build = memset + morton/hist + 4 onesweep passes + emit",
+            "roofline_build": {"bound": "hbm", "stage": "build = memset + morton keys + cooperative 4-pass radix sort + emit",
                                "achieved": build_gbs, "peak": peak, "unit": "GB/s", "frac": build_gbs / peak,
                                "algorithmic_bytes_per_build": build_bytes, "ms_per_build": build_ms},
         }
