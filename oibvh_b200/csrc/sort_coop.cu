@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
         __syncthreads();
 
         COOP_STAMP(2);
-        // ---- per digit: warp-exclusive offsets, CTA count -> counts[digit][cta] ----
-        uint32_t cta_count = 0;
+        // ---- per digit: warp-exclusive offsets, CTA count -> counts[digit][cta]; local slot bases ----
+        // Everything that needs only this CTA's data happens BEFORE the first grid barrier (it overlaps with waiting
+        // for the slowest CTA): the exclusive scan of the CTA's digit counts and the reorder into shared memory.
+        uint32_t cta_count = 0, digit_base = 0;
         if (tid < kCoopRadix)
         {
             uint32_t run = 0;
@@ -129,6 +131,36 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             }
             cta_count = run;
             mat[(size_t)tid * G + cta] = cta_count;
+            uint32_t inc = cta_count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += n;
+            }
+            if (lane == 31) sm.scan[warp] = inc;
+            digit_base = inc - cta_count; // + totals of the lower warps, added below
+        }
+        __syncthreads();
+        if (tid < kCoopRadix)
+        {
+#pragma unroll
+            for (int w = 0; w < kCoopRadix / 32; w++)
+                if ((uint32_t)w < warp) digit_base += sm.scan[w];
+            // fold the CTA-level digit base into the per-warp offsets: slot = rank_tab[warp][d].x + rank
+#pragma unroll
+            for (int w = 0; w < kCoopWarps; w++) sm.rank_tab[w][tid].x += digit_base;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kCoopIptMax; j++)
+        {
+            const uint32_t i = warp_base + j * 32 + lane;
+            if ((uint32_t)j < ipt && i < T)
+            {
+                const uint32_t d = (key[j] >> shift) & MASK;
+                sm.kv[my_tab[d].x + rank[j]] = make_uint2(key[j], val[j]);
+            }
         }
         COOP_STAMP(3);
         grid_sync(ctl, ++gen, ctl + 1);
@@ -172,67 +204,34 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
         grid_sync(ctl, ++gen, ctl + 1);
         COOP_STAMP(6);
 
-        // ---- global base of every digit for this CTA ----
-        uint32_t col = 0, tot = 0;
+        // ---- global base of every digit for this CTA: (scan of the row totals) + (row prefix at this CTA) ----
         if (tid < kCoopRadix)
         {
-            col = __ldcg(mat + (size_t)tid * G + cta);
-            tot = __ldcg(totals + tid);
-        }
-        // exclusive scans over the 256 digits of (row totals -> bin start) and (CTA counts -> slot base), fused:
-        // warp scans of both values, then the 8 warp totals
-        uint32_t inc_t = tot, inc_c = cta_count;
-        if (tid < kCoopRadix)
-        {
+            const uint32_t col = __ldcg(mat + (size_t)tid * G + cta);
+            const uint32_t tot = __ldcg(totals + tid);
+            uint32_t inc = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
             {
-                const uint32_t a = __shfl_up_sync(0xffffffffu, inc_t, o), b = __shfl_up_sync(0xffffffffu, inc_c, o);
-                if (lane >= (uint32_t)o)
-                {
-                    inc_t += a;
-                    inc_c += b;
-                }
+                const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += n;
             }
-            if (lane == 31)
-            {
-                sm.scan[warp] = inc_t;
-                sm.scan[8 + warp] = inc_c;
-            }
+            if (lane == 31) sm.scan[warp] = inc;
+            sm.global_base[tid] = inc - tot + col - digit_base; // + totals of the lower warps, added below
         }
         __syncthreads();
         if (tid < kCoopRadix)
         {
-            uint32_t base_t = 0, base_c = 0;
+            uint32_t base = 0;
 #pragma unroll
             for (int w = 0; w < kCoopRadix / 32; w++)
-                if ((uint32_t)w < warp)
-                {
-                    base_t += sm.scan[w];
-                    base_c += sm.scan[8 + w];
-                }
-            const uint32_t bin_start = base_t + inc_t - tot;
-            const uint32_t digit_base = base_c + inc_c - cta_count;
-            sm.global_base[tid] = bin_start + col - digit_base;
-            // fold the CTA-level digit base into the per-warp offsets: slot = rank_tab[warp][d].x + rank
-#pragma unroll
-            for (int w = 0; w < kCoopWarps; w++) sm.rank_tab[w][tid].x += digit_base;
+                if ((uint32_t)w < warp) base += sm.scan[w];
+            sm.global_base[tid] += base;
         }
         __syncthreads();
 
         COOP_STAMP(7);
-        // ---- reorder inside the chunk through shared memory, then write digit runs coalesced ----
-#pragma unroll
-        for (int j = 0; j < kCoopIptMax; j++)
-        {
-            const uint32_t i = warp_base + j * 32 + lane;
-            if ((uint32_t)j < ipt && i < T)
-            {
-                const uint32_t d = (key[j] >> shift) & MASK;
-                sm.kv[my_tab[d].x + rank[j]] = make_uint2(key[j], val[j]);
-            }
-        }
-        __syncthreads();
+        // ---- write digit runs coalesced ----
 #pragma unroll
         for (int k = 0; k < kCoopIptMax; k++)
         {
