@@ -248,8 +248,7 @@ def run_gpu_arm(args):
     scene.set_shard(rank, world)
 
     def frame():
-        tree_a.build()
-        tree_b.build()
+        ob.build_many([tree_a, tree_b])
         tree_b.transform(M_rot)
         tree_a.refit(upload=False)
         tree_b.refit(upload=False)
@@ -349,8 +348,7 @@ def run_gpu_arm(args):
     def e2e_frame(i):
         tree_a.set_positions_from_host_ptr(host_a.data_ptr())
         tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
-        tree_a.build()
-        tree_b.build()
+        ob.build_many([tree_a, tree_b])
         tree_a.refit(upload=False)
         tree_b.refit(upload=False)
         scene.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)

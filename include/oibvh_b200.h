@@ -122,6 +122,10 @@ int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const float* dev_posi
 int oibvh_tree_transform(oibvh_tree* tree, const float M[16]);
 /* OibvhTree::build (src/cuda/oibvhTree.cu:237-388): Morton keys, stable sort, implicit-layout AABB reduction */
 int oibvh_tree_build(oibvh_tree* tree);
+/* Build several trees of the same context together (extension; the reference builds one tree per call): the keys of
+ * all trees are sorted by ONE cooperative launch, which costs the grid barriers of a single sort. Falls back to
+ * consecutive oibvh_tree_build calls when the trees do not fit one launch. Results are identical to separate builds. */
+int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n);
 /* OibvhTree::refit (src/cuda/oibvhTree.cu:193-235) on the positions currently on the device */
 int oibvh_tree_refit(oibvh_tree* tree);
 /* getPrimCount / vertex count / oibvh_get_size(T) / getDepth() = ilog2(N)  (oibvhTree.cu:45-53) */

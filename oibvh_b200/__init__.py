@@ -69,6 +69,7 @@ _SIGNATURES = {
     "oibvh_tree_set_positions_from_device": (C.c_int, [_vp, _vp]),
     "oibvh_tree_transform": (C.c_int, [_vp, _f32p]),
     "oibvh_tree_build": (C.c_int, [_vp]),
+    "oibvh_tree_build_many": (C.c_int, [C.POINTER(_vp), _u32]),
     "oibvh_tree_refit": (C.c_int, [_vp]),
     "oibvh_tree_get_info": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
     "oibvh_tree_is_built": (C.c_int, [_vp, C.POINTER(C.c_int)]),
@@ -470,6 +471,14 @@ class OibvhTree:
         a, b, c = _vp(), _vp(), _vp()
         _check(_lib.oibvh_tree_device_views(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+def build_many(trees):
+    """build several trees together: one cooperative launch sorts all their keys (oibvh_tree_build_many)"""
+    arr = (_vp * len(trees))(*[t._h for t in trees])
+    _check(_lib.oibvh_tree_build_many(arr, len(trees)))
+    for t in trees:
+        t.m_buildDone = True
 
 
 # =====================================================================================================

@@ -641,6 +641,73 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     return OIBVH_OK;
 }
 
+extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
+{
+    REQUIRE(trees != nullptr && n >= 1, "no trees");
+    for (uint32_t i = 0; i < n; i++) REQUIRE(trees[i] != nullptr, "NULL tree");
+    oibvh_ctx* ctx = trees[0]->ctx;
+    uint64_t total = 0;
+    bool batch = n >= 2 && n <= 4;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
+        total += trees[i]->T;
+    }
+    // every tree must still get enough CTAs for <= 16 keys per thread; the launcher re-checks and refuses otherwise
+    if (batch && total > coop_sort_capacity_multi()) batch = false;
+    if (!batch)
+    {
+        for (uint32_t i = 0; i < n; i++)
+        {
+            int rc = oibvh_tree_build(trees[i]);
+            if (rc) return rc;
+        }
+        return OIBVH_OK;
+    }
+    DeviceGuard g(ctx->device);
+    StageScope scope(ctx, OIBVH_STAGE_BUILD);
+    cudaStream_t s = ctx->stream;
+    uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
+    for (uint32_t i = 0; i < n; i++)
+    {
+        oibvh_tree* t = trees[i];
+        CU(cudaMemsetAsync(t->sort_ctl, 0, 64 * sizeof(uint32_t), s));
+        CU(launch_morton_hist(t->faces_in, t->pos, t->T, t->mesh, t->keys_a, nullptr, s));
+        count_launch(ctx);
+        ka[i] = t->keys_a; kb[i] = t->keys_b; va[i] = t->vals_a; vb[i] = t->vals_b; ctl[i] = t->sort_ctl; T[i] = t->T;
+    }
+    cudaError_t e = launch_coop_sort_many(n, ka, kb, va, vb, T, ctl, s);
+    if (e == cudaErrorInvalidValue)
+    {
+        // very unequal sizes: sort one by one (keys are already computed)
+        cudaGetLastError();
+        for (uint32_t i = 0; i < n; i++)
+        {
+            oibvh_tree* t = trees[i];
+            if (t->T <= coop_sort_capacity())
+            {
+                CU(launch_coop_sort(t->keys_a, t->keys_b, t->vals_a, t->vals_b, t->T, t->sort_ctl, s));
+                count_launch(ctx);
+            }
+            else
+                return fail(OIBVH_ERR_INTERNAL, "build_many: tree %u does not fit the cooperative sort", i);
+        }
+    }
+    else
+    {
+        CU(e);
+        count_launch(ctx);
+    }
+    for (uint32_t i = 0; i < n; i++)
+    {
+        oibvh_tree* t = trees[i];
+        CU(launch_tree_emit(true, t->faces_in, t->vals_a, t->faces, t->pos, t->nodes, t->T, t->done_counter, s));
+        count_launch(ctx);
+        t->built = true;
+    }
+    return OIBVH_OK;
+}
+
 extern "C" int oibvh_tree_refit(oibvh_tree* tree)
 {
     REQUIRE(tree != nullptr, "tree is NULL");

@@ -37,6 +37,11 @@ cudaError_t launch_onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_i
 cudaError_t coop_sort_configure();
 uint32_t coop_sort_capacity(); // largest T the cooperative kernel takes on this device
 size_t coop_sort_ctl_words();
+uint32_t coop_sort_capacity_multi(); // total keys of a multi-array launch (longer per-CTA chunks)
+// n <= 4 arrays side by side in one launch (shared grid barriers); cudaErrorInvalidValue if they do not fit one wave.
+// The first 64 words of ctl[0] must be zero (barrier state); every ctl[i] holds that array's counts.
+cudaError_t launch_coop_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
+                                  uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s);
 cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
                              uint32_t* ctl, cudaStream_t s);
 cudaError_t tree_emit_configure();

@@ -13,14 +13,16 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace oibvh
 {
 
 constexpr int kCoopThreads = 512;
 constexpr int kCoopWarps = kCoopThreads / 32;
-constexpr int kCoopIptMax = 8;
+constexpr int kCoopIptSingle = 8;  // one tree over the whole grid
+constexpr int kCoopIptMulti = 16;  // several trees side by side: fewer CTAs each, longer chunks
 constexpr int kCoopRadix = 1 << kRadixBits; // 256
-constexpr int kCoopTileMax = kCoopThreads * kCoopIptMax; // 4096 keys per CTA
 constexpr int kCoopRowSeg = 10;                          // row scan: entries per lane -> grids up to 320 CTAs
 // two CTAs of 512 threads per SM measured faster than one of 1024 (shorter block-level phases)
 
@@ -44,23 +46,49 @@ extern "C" int oibvh_debug_coop_profile(unsigned long long* out)
 #define COOP_STAMP(k)
 #endif
 
+template <int IPT_MAX>
 struct CoopSmem
 {
     uint2 rank_tab[kCoopWarps][kCoopRadix]; // ranking: (.x running count, .y peer mask); afterwards .x = slot base
-    uint2 kv[kCoopTileMax];                 // reorder phase: (key, value) by slot
+    uint2 kv[kCoopThreads * IPT_MAX];       // reorder phase: (key, value) by slot
     uint32_t global_base[kCoopRadix];
     uint32_t scan[16];
 };
 
-__global__ void __launch_bounds__(kCoopThreads, 2)
-    coop_sort_kernel(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T, uint32_t ipt,
-                     uint32_t* ctl)
+// One sort job inside a launch: a contiguous range of CTAs works on one (key, value) array. Several trees are
+// sorted by ONE launch (CTA ranges side by side, shared grid barriers), which costs the barriers of one sort.
+struct SortSeg
+{
+    uint32_t *keys_a, *keys_b, *vals_a, *vals_b;
+    uint32_t* ctl; // this job's totals / counts block
+    uint32_t T, ipt, cta0, ncta;
+};
+constexpr int kMaxSortSegs = 4;
+struct SortSegs
+{
+    SortSeg s[kMaxSortSegs];
+    uint32_t n;
+};
+
+template <int IPT_MAX>
+__global__ void __launch_bounds__(kCoopThreads, 2) coop_sort_kernel(const SortSegs segs, uint32_t* sync_ctl)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoopSmem& sm = *reinterpret_cast<CoopSmem*>(smem_raw);
+    CoopSmem<IPT_MAX>& sm = *reinterpret_cast<CoopSmem<IPT_MAX>*>(smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const uint32_t cta = blockIdx.x, G = gridDim.x;
+    uint32_t si = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxSortSegs; i++)
+        if ((uint32_t)i < segs.n && blockIdx.x >= segs.s[i].cta0) si = i;
+    const SortSeg& seg = segs.s[si];
+    uint32_t* const keys_a = seg.keys_a;
+    uint32_t* const keys_b = seg.keys_b;
+    uint32_t* const vals_a = seg.vals_a;
+    uint32_t* const vals_b = seg.vals_b;
+    uint32_t* const ctl = seg.ctl;
+    const uint32_t T = seg.T, ipt = seg.ipt;
+    const uint32_t cta = blockIdx.x - seg.cta0, G = seg.ncta;
     const uint32_t chunk = kCoopThreads * ipt;
     const uint32_t cta_base = cta * chunk;
     const uint32_t cta_valid = cta_base < T ? min(chunk, T - cta_base) : 0u;
@@ -76,15 +104,14 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
         constexpr uint32_t MASK = kCoopRadix - 1;
         COOP_STAMP(0);
         // ---- load this CTA's chunk (written by other SMs in the previous pass: through L2) ----
-        uint32_t key[kCoopIptMax], val[kCoopIptMax];
-        uint16_t rank[kCoopIptMax];
+        uint32_t key[IPT_MAX];
+        uint16_t rank[IPT_MAX];
 #pragma unroll
-        for (int j = 0; j < kCoopIptMax; j++)
+        for (int j = 0; j < IPT_MAX; j++)
         {
             const uint32_t i = warp_base + j * 32 + lane;
             const bool valid = (uint32_t)j < ipt && i < T;
             key[j] = valid ? __ldcg(kin + i) : 0xffffffffu;
-            val[j] = (valid && vin) ? __ldcg(vin + i) : i; // first pass: the value is the face id
         }
         for (int i = tid; i < kCoopWarps * kCoopRadix; i += kCoopThreads) (&sm.rank_tab[0][0])[i] = make_uint2(0u, 0u);
         __syncthreads();
@@ -94,7 +121,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
         uint2* my_tab = sm.rank_tab[warp];
         const uint32_t lane_bit = 1u << lane;
 #pragma unroll
-        for (int j = 0; j < kCoopIptMax; j++)
+        for (int j = 0; j < IPT_MAX; j++)
         {
             if ((uint32_t)j < ipt) // warp-uniform
             {
@@ -152,25 +179,26 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             for (int w = 0; w < kCoopWarps; w++) sm.rank_tab[w][tid].x += digit_base;
         }
         __syncthreads();
+        // values are fetched only now (registers stay free during ranking); first pass: the value is the face id
 #pragma unroll
-        for (int j = 0; j < kCoopIptMax; j++)
+        for (int j = 0; j < IPT_MAX; j++)
         {
             const uint32_t i = warp_base + j * 32 + lane;
             if ((uint32_t)j < ipt && i < T)
             {
+                const uint32_t val = vin ? __ldcg(vin + i) : i;
                 const uint32_t d = (key[j] >> shift) & MASK;
-                sm.kv[my_tab[d].x + rank[j]] = make_uint2(key[j], val[j]);
+                sm.kv[my_tab[d].x + rank[j]] = make_uint2(key[j], val);
             }
         }
         COOP_STAMP(3);
-        grid_sync(ctl, ++gen, ctl + 1);
+        grid_sync(sync_ctl, ++gen, sync_ctl + 1);
         COOP_STAMP(4);
 
         // ---- one warp scans each digit row (exclusive prefix over CTAs) and records the row total ----
         {
-            // rows cta, cta + G, ... : one warp each
-            const uint32_t r = cta + warp * G;
-            if (r < (uint32_t)kCoopRadix)
+            // digit rows are dealt to the warps of this job's CTAs (a job with few CTAs takes several per warp)
+            for (uint32_t r = cta + warp * G; r < (uint32_t)kCoopRadix; r += G * kCoopWarps)
             {
                 uint32_t* row = mat + (size_t)r * G;
                 uint32_t v[kCoopRowSeg];
@@ -201,7 +229,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             }
         }
         COOP_STAMP(5);
-        grid_sync(ctl, ++gen, ctl + 1);
+        grid_sync(sync_ctl, ++gen, sync_ctl + 1);
         COOP_STAMP(6);
 
         // ---- global base of every digit for this CTA: (scan of the row totals) + (row prefix at this CTA) ----
@@ -233,7 +261,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
         COOP_STAMP(7);
         // ---- write digit runs coalesced ----
 #pragma unroll
-        for (int k = 0; k < kCoopIptMax; k++)
+        for (int k = 0; k < IPT_MAX; k++)
         {
             const uint32_t s = tid + k * kCoopThreads;
             if (s < cta_valid)
@@ -245,7 +273,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2)
             }
         }
         COOP_STAMP(8);
-        if (pass + 1 < kRadixPasses) grid_sync(ctl, ++gen, ctl + 1);
+        if (pass + 1 < kRadixPasses) grid_sync(sync_ctl, ++gen, sync_ctl + 1);
         COOP_STAMP(9);
         // ping-pong
         uint32_t* nk = kout;
@@ -261,36 +289,71 @@ static int g_coop_sort_grid = 0;
 
 cudaError_t coop_sort_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(coop_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(CoopSmem));
+    cudaError_t e = cudaFuncSetAttribute(coop_sort_kernel<kCoopIptSingle>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(CoopSmem<kCoopIptSingle>));
     if (e != cudaSuccess) return e;
-    int per_sm = 0, sms = 0, dev = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_sort_kernel, kCoopThreads, sizeof(CoopSmem));
+    e = cudaFuncSetAttribute(coop_sort_kernel<kCoopIptMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CoopSmem<kCoopIptMulti>));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, per_sm_multi = 0, sms = 0, dev = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_sort_kernel<kCoopIptSingle>, kCoopThreads,
+                                                      sizeof(CoopSmem<kCoopIptSingle>));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_multi, coop_sort_kernel<kCoopIptMulti>, kCoopThreads,
+                                                      sizeof(CoopSmem<kCoopIptMulti>));
     if (e != cudaSuccess) return e;
     e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    int grid = sms * (per_sm >= 2 ? 2 : 1);
+    if (per_sm < 1 || per_sm_multi < 1) return cudaErrorLaunchOutOfResources;
+    int grid = sms * (std::min(per_sm, per_sm_multi) >= 2 ? 2 : 1);
     if (grid > 32 * kCoopRowSeg) grid = 32 * kCoopRowSeg; // row scan covers at most 320 CTAs
     g_coop_sort_grid = grid;
     return cudaSuccess;
 }
 
-uint32_t coop_sort_capacity() { return (uint32_t)g_coop_sort_grid * kCoopTileMax; }
+uint32_t coop_sort_capacity() { return (uint32_t)g_coop_sort_grid * kCoopThreads * kCoopIptSingle; }
+uint32_t coop_sort_capacity_multi() { return (uint32_t)g_coop_sort_grid * kCoopThreads * kCoopIptMulti; }
 size_t coop_sort_ctl_words() { return (size_t)kCoopCtlMat + (size_t)kCoopRadix * 32 * kCoopRowSeg; }
+
+// Sort n <= 4 arrays in one cooperative launch. CTAs are dealt in proportion to the sizes. Returns
+// cudaErrorInvalidValue when the arrays do not fit one wave (the caller then sorts them one by one / streams).
+cudaError_t launch_coop_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
+                                  uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s)
+{
+    if (n == 0 || n > (uint32_t)kMaxSortSegs) return cudaErrorInvalidValue;
+    const uint32_t G = (uint32_t)g_coop_sort_grid;
+    SortSegs segs;
+    segs.n = n;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += T[i];
+    uint32_t next = 0, max_ipt = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        uint32_t ncta = (i + 1 == n) ? G - next : (uint32_t)std::max<uint64_t>(1, (uint64_t)G * T[i] / total);
+        if (next + ncta > G || ncta == 0) return cudaErrorInvalidValue;
+        uint32_t ipt = (T[i] + ncta * kCoopThreads - 1) / (ncta * kCoopThreads);
+        if (ipt == 0) ipt = 1;
+        max_ipt = std::max(max_ipt, ipt);
+        segs.s[i] = SortSeg{keys_a[i], keys_b[i], vals_a[i], vals_b[i], ctl[i], T[i], ipt, next, ncta};
+        next += ncta;
+    }
+    uint32_t* sync_ctl = ctl[0];
+    void* args[] = {&segs, &sync_ctl};
+    if (max_ipt <= (uint32_t)kCoopIptSingle)
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(coop_sort_kernel<kCoopIptSingle>), dim3(G),
+                                           dim3(kCoopThreads), args, sizeof(CoopSmem<kCoopIptSingle>), s);
+    if (max_ipt <= (uint32_t)kCoopIptMulti)
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(coop_sort_kernel<kCoopIptMulti>), dim3(G),
+                                           dim3(kCoopThreads), args, sizeof(CoopSmem<kCoopIptMulti>), s);
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
                              uint32_t* ctl, cudaStream_t s)
 {
-    const uint32_t G = (uint32_t)g_coop_sort_grid;
-    uint32_t ipt = (T + G * kCoopThreads - 1) / (G * kCoopThreads);
-    if (ipt == 0) ipt = 1;
-    if (ipt > (uint32_t)kCoopIptMax) return cudaErrorInvalidValue;
-    void* args[] = {&keys_a, &keys_b, &vals_a, &vals_b, &T, &ipt, &ctl};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(coop_sort_kernel), dim3(G), dim3(kCoopThreads),
-                                       args, sizeof(CoopSmem), s);
+    return launch_coop_sort_many(1, &keys_a, &keys_b, &vals_a, &vals_b, &T, &ctl, s);
 }
 
 } // namespace oibvh

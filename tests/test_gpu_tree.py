@@ -144,3 +144,25 @@ def test_errors(ctx):
         sc.addOibvhTree(t)  # Scene::addOibvhTree asserts m_buildDone (scene.cu:97)
     with pytest.raises(ob.OibvhError):
         sc.detectCollision(ob.DeviceType.CPU)
+
+
+def test_build_many_equals_separate_builds(ctx, port):
+    """oibvh_tree_build_many sorts the keys of several trees in one cooperative launch: same results"""
+    specs = [(meshgen.blob(300, 200, seed=21), None), (meshgen.blob(160, 110, seed=22), 30001),
+             (meshgen.icosphere(4), None)]
+    trees, wants = [], []
+    for (pos, faces), cut in specs:
+        faces = meshgen.shuffle_faces(faces)
+        if cut:
+            faces = np.ascontiguousarray(faces[:cut])
+        mesh = ob.Mesh(pos, faces)
+        trees.append(ob.OibvhTree(mesh, ctx=ctx))
+        wants.append(port.build(pos, faces, mesh.m_aabb))
+    ob.build_many(trees)
+    for t, w in zip(trees, wants):
+        d = t.download()
+        assert np.array_equal(t.sorted_keys(), w["keys"])
+        assert np.array_equal(d["perm"], w["perm"])
+        assert_bit_equal(d["nodes"], w["nodes"], "build_many nodes")
+    ob.build_many(trees[:1])  # n = 1 falls back to a plain build
+    assert_bit_equal(trees[0].download()["nodes"], wants[0]["nodes"], "build_many(1)")
