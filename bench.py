@@ -422,7 +422,8 @@ def run_gpu_arm(args):
                          "frac": refit_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": refit_bytes, "ms_per_launch": refit_ms,
                          "timing": "CUDA events around the launch, eager second pass over the same K frames"},
-            "roofline_build": {"bound": "hbm", "stage": "build = memset + morton keys + cooperative 4-pass radix sort + emit",
+            "stage_share": {k: (v / sum(stage.values()) if sum(stage.values()) > 0 else 0.0) for k, v in stage.items()},
+            "roofline_build": {"bound": "hbm", "stage": "build (per tree) = morton keys + cooperative 4-pass radix sort (both trees in one launch) + emit",
                                "achieved": build_gbs, "peak": peak, "unit": "GB/s", "frac": build_gbs / peak,
                                "algorithmic_bytes_per_build": build_bytes, "ms_per_build": build_ms},
         }

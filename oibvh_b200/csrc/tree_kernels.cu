@@ -94,7 +94,13 @@ __device__ __forceinline__ uint32_t morton_of_box(const Box& b, const MeshAabb& 
     return (spread3(quantise10(qx)) << 2) | (spread3(quantise10(qy)) << 1) | spread3(quantise10(qz));
 }
 
-constexpr int kMortonFacesPerThread = 4;
+#ifndef OIBVH_MORTON_FPT
+#define OIBVH_MORTON_FPT 4
+#endif
+#ifndef OIBVH_MORTON_CTAS_PER_SM
+#define OIBVH_MORTON_CTAS_PER_SM 5
+#endif
+constexpr int kMortonFacesPerThread = OIBVH_MORTON_FPT;
 
 template <int RADIX_BITS, int PASSES, bool HIST>
 __global__ void __launch_bounds__(256) morton_hist_kernel(const uint4* __restrict__ faces4,
@@ -373,12 +379,16 @@ struct LevelTable
     uint32_t cnt[32]; // nodes kept at level l
 };
 
-constexpr int kEmitThreads = 256;
+#ifndef OIBVH_EMIT_THREADS
+#define OIBVH_EMIT_THREADS 256
+#endif
+constexpr int kEmitThreads = OIBVH_EMIT_THREADS;
 constexpr int kEmitWarps = kEmitThreads / 32;
 constexpr int kLeavesPerThread = 4;
 constexpr int kWarpLeaves = 32 * kLeavesPerThread;      // 128
 constexpr int kChunk = kEmitThreads * kLeavesPerThread; // 1024 leaves
-constexpr int kChunkLevels = 10;                        // log2(kChunk)
+constexpr int kChunkLevels = kEmitThreads == 256 ? 10 : (kEmitThreads == 128 ? 9 : (kEmitThreads == 512 ? 11 : 8)); // log2(kChunk)
+static_assert((1 << kChunkLevels) == kChunk, "chunk must be a power of two");
 constexpr int kWarpLevels = 7;                          // log2(kWarpLeaves)
 
 // slot of the first height-h node inside a warp's staging area (h = 1..7): 0, 64, 96, 112, 120, 124, 126
@@ -673,7 +683,7 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
     if (warp == 0)
     {
         // s_top slots: height 7: [0,8), 8: [8,12), 9: [12,14), 10: [14,15)
-        int src = 0, dstb = 8;
+        int src = 0, dstb = kEmitWarps;
 #pragma unroll
         for (int h = kWarpLevels + 1; h <= kChunkLevels; h++)
         {
@@ -794,7 +804,7 @@ cudaError_t launch_morton_hist(const uint4* faces4, const float4* pos4, uint32_t
 {
     const uint32_t tile = 256 * kMortonFacesPerThread;
     uint32_t blocks = (T + tile - 1) / tile;
-    const uint32_t cap = kNumSMsB200 * 5; // 48 registers -> 5 resident CTAs per SM
+    const uint32_t cap = kNumSMsB200 * OIBVH_MORTON_CTAS_PER_SM; // persistent: one wave of resident CTAs
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     if (hist)
