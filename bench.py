@@ -250,8 +250,8 @@ def run_gpu_arm(args):
     def frame():
         ob.build_many([tree_a, tree_b])
         tree_b.transform(M_rot)
+        tree_b.refit(upload=False)  # B first: its faces / positions are the freshest lines in L2 after the build
         tree_a.refit(upload=False)
-        tree_b.refit(upload=False)
         scene.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
 
     def barrier():

@@ -107,3 +107,26 @@ def test_streaming_sort_path_beyond_single_wave(ctx, port):
     assert np.array_equal(t.sorted_keys(), o["keys"])
     assert np.array_equal(d["perm"], o["perm"])
     assert_bit_equal(d["nodes"], o["nodes"], "1.5M build")
+
+
+def test_six_hundred_cubes(ctx, port):
+    """well past the reference's 256-object limit (collide.cu:91-93): 600 cubes, 179 700 object pairs seeded on the
+    device, most pruned by the root test in round 0"""
+    rng = np.random.default_rng(3)
+    meshes = []
+    for k in range(600):
+        c = rng.uniform(-4.0, 4.0, size=3)
+        p, f = meshgen.cube(0.3, c)
+        meshes.append((p, f))
+    want, ncand, _ = oracle_scene(port, meshes)
+    sc = ob.Scene(ctx)
+    keep = []
+    for p, f in meshes:
+        t = ob.OibvhTree(ob.Mesh(p, f), ctx=ctx)
+        t.build()
+        sc.addOibvhTree(t)
+        keep.append(t)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 0)
+    assert sc.getCandidateCount() == ncand
+    assert np.array_equal(sc.canonical_pairs(), want)
+    assert len({tuple(r) for r in want[:, :2].tolist()}) > 50
