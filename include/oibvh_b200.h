@@ -153,7 +153,8 @@ int oibvh_scene_add_tree(oibvh_scene* scene, oibvh_tree* tree);
 int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world);
 /* Scene::detectCollision(GPUx, entryLevel, expandLevels) (src/cuda/scene.cu:157-185, 225-446): broad + narrow phase
  * over all object pairs i<j. entry_level / expand_levels keep the reference meaning (seed level; levels descended
- * per round, 0 = choose adaptively); the resulting pair SET does not depend on them.
+ * per round); expand_levels = 0 lets the library choose the schedule (3 levels per round, round 0 absorbs the
+ * remainder, entry_level ignored). The resulting pair SET does not depend on either value.
  * n_candidates may be NULL. Synchronises. */
 int oibvh_scene_detect(oibvh_scene* scene, uint32_t entry_level, uint32_t expand_levels, uint32_t* n_pairs,
                        uint32_t* n_candidates);

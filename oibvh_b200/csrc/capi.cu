@@ -892,19 +892,30 @@ static int scene_upload_objs(oibvh_scene* s)
 
 static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_levels)
 {
+    const uint32_t requested_expand = expand_levels;
     oibvh_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t n_obj = (uint32_t)s->trees.size();
     uint32_t maxL = 0;
     for (auto* t : s->trees) maxL = std::max(maxL, t->L);
-    // expand_levels == 0: the kernel picks 2..4 levels per round from the front size; `rounds` is then only an upper
-    // bound (the kernel stops as soon as a front is empty). One warp tests the 4^k descendant pairs of a node pair.
-    expand_levels = std::min(expand_levels, 4u);
-    // round 0 descends from the roots to the entry level (a hint: the pair set does not depend on it)
-    const uint32_t k0 = entry_level > 0 ? std::min(entry_level, 5u) : (expand_levels ? expand_levels : 4u);
+    // One warp tests the 4^k descendant pairs of a node pair, 64 per iteration, so k = 3 costs one iteration per pair.
+    // The fronts grow geometrically towards the leaves; the cheapest schedule (measured) makes EVERY round after the
+    // first a 3-level round -- in particular the last, widest one -- and lets round 0 absorb the remainder.
+    // expand_levels == 0 selects that schedule (entry_level is then ignored: both are hints, the pair set does not
+    // depend on them); explicit values are honoured up to 5 (round 0) / 4 levels.
+    uint32_t k0;
+    if (expand_levels == 0)
+    {
+        expand_levels = 3;
+        k0 = maxL <= 5 ? maxL : 3 + (maxL - 3) % 3;
+    }
+    else
+    {
+        expand_levels = std::min(expand_levels, 4u);
+        k0 = entry_level > 0 ? std::min(entry_level, 5u) : expand_levels;
+    }
     const uint32_t reached = std::min(k0, maxL);
-    const uint32_t kmin = expand_levels ? expand_levels : 2u;
-    const uint32_t rounds = 1 + (maxL - reached + kmin - 1) / kmin; // leaf pairs leave as candidates
+    const uint32_t rounds = 1 + (maxL - reached + expand_levels - 1) / expand_levels; // leaf pairs leave as candidates
     if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
 
     CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));
@@ -918,7 +929,7 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     }
     CU(cudaMemcpyAsync(s->h_counters, s->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost, st));
     s->last_entry = entry_level;
-    s->last_expand = expand_levels;
+    s->last_expand = requested_expand;
     s->last_rounds = rounds;
     s->detect_pending = true;
     s->enqueue_generation = ctx->generation;

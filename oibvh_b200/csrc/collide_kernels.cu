@@ -40,6 +40,17 @@ __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, ui
 // Round 0 of the expansion turns them into the reference's entry-level seed rectangle (scene.cu:192-223)
 // and prunes object pairs whose root boxes do not overlap.
 // ---------------------------------------------------------------------------------------------------
+// p-th object pair (i < j), row-major over the strict upper triangle of the n_obj x n_obj matrix
+__device__ __forceinline__ uint4 seed_entry(uint32_t n_obj, uint64_t p)
+{
+    const double nd = (double)n_obj;
+    uint32_t i = (uint32_t)floor((2.0 * nd - 1.0 - sqrt((2.0 * nd - 1.0) * (2.0 * nd - 1.0) - 8.0 * (double)p)) * 0.5);
+    while ((uint64_t)i * (2ull * n_obj - i - 1) / 2 > p) i--; // fix the rounding of the closed form
+    while ((uint64_t)(i + 1) * (2ull * n_obj - i - 2) / 2 <= p) i++;
+    const uint32_t j = (uint32_t)(p - (uint64_t)i * (2ull * n_obj - i - 1) / 2) + i + 1;
+    return make_uint4(i, j, 0u, 0u);
+}
+
 __device__ void seed_phase(uint32_t n_obj, uint4* __restrict__ front, uint32_t front_cap,
                            uint32_t* __restrict__ counters)
 {
@@ -136,10 +147,12 @@ __device__ __forceinline__ LevelView level_view(const uint32_t* s_lv, uint32_t o
 __device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32_t* s_lv,
                              const ObjDesc* __restrict__ objs, const uint4* in, uint4* out, uint32_t front_cap,
                              uint4* cand, uint32_t cand_cap, uint32_t* counters, uint32_t round, uint32_t front_size,
-                             uint32_t levels, uint32_t rank, uint32_t world)
+                             uint32_t levels, uint32_t rank, uint32_t world, uint32_t n_obj)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t n = min(front_size, front_cap);
+    // round 0 of a scene with few object pairs computes its entries (root pairs) instead of reading a seeded front
+    const bool computed_seeds = (round == 0 && in == nullptr);
+    const uint32_t n = computed_seeds ? front_size : min(front_size, front_cap);
     uint32_t* next_count = counters + CTR_FRONT0 + round + 1;
     const uint32_t total_warps = gridDim.x * kColWarps;
     uint4* stage = s_stage + warp * kStageCap;
@@ -170,12 +183,13 @@ __device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32
     // fronts are produced by other SMs inside this same launch: read them through L2 (ld.cg); the entry of the
     // NEXT item is fetched before the current one is processed (one round trip off the critical path)
     uint4 it_next = make_uint4(0, 0, 0, 0);
-    if (w < items) it_next = __ldcg(in + (w >> gshift));
+    auto entry = [&](uint32_t p) { return computed_seeds ? seed_entry(n_obj, p) : __ldcg(in + p); };
+    if (w < items) it_next = entry(w >> gshift);
     for (; w < items; w += total_warps)
     {
         const uint4 it = it_next;
         const uint32_t p = w >> gshift, group = w & ((1u << gshift) - 1);
-        if (w + total_warps < items) it_next = __ldcg(in + ((w + total_warps) >> gshift));
+        if (w + total_warps < items) it_next = entry((w + total_warps) >> gshift);
         const ObjDesc A = get_obj(s_objs, objs, it.x), B = get_obj(s_objs, objs, it.y);
         const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
         const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
@@ -381,24 +395,37 @@ __global__ void __launch_bounds__(kColThreads, 1)
     }
     __syncthreads();
     uint32_t gen = 0;
-    auto stamp = [&](uint32_t i) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && i < CTR_WORDS - CTR_TIME0) counters[CTR_TIME0 + i] = (uint32_t)clock64();
+    uint32_t n_stamps = 0;
+    auto stamp = [&](uint32_t) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < CTR_WORDS - CTR_TIME0)
+            counters[CTR_TIME0 + n_stamps] = (uint32_t)clock64();
+        n_stamps++;
     };
     stamp(0);
-    seed_phase(n_obj, front0, front_cap, counters);
-    uint32_t front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0);
-    stamp(gen);
+    // few object pairs (the common two-body scene): round 0 computes the root pairs on the fly, which saves the seeding
+    // pass and its grid barrier; many-body scenes seed the front in parallel first
+    const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
+    const bool computed_seeds = n_pairs <= 4096;
+    uint32_t front_size;
+    if (computed_seeds)
+    {
+        front_size = (uint32_t)n_pairs;
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FRONT0] = front_size;
+    }
+    else
+    {
+        seed_phase(n_obj, front0, front_cap, counters);
+        front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0);
+    }
+    stamp(1);
     for (uint32_t r = 0; r < rounds && front_size != 0; r++) // front_size is uniform over the grid
     {
         uint4* in = (r & 1) ? front1 : front0;
         uint4* out = (r & 1) ? front0 : front1;
-        // levels == 0: adaptive. Small fronts are latency-bound (one barrier per round): descend 4 levels per
-        // round; large fronts are throughput-bound: fewer levels prune earlier and test far fewer box pairs.
-        // front_size is uniform over the grid, so every CTA picks the same value.
-        uint32_t k = r == 0 ? levels0 : levels;
-        if (k == 0) k = front_size < 4096u ? 4u : (front_size < 32768u ? 3u : 2u);
+        if (r == 0 && computed_seeds) in = nullptr;
+        const uint32_t k = r == 0 ? levels0 : levels; // schedule chosen by the host (see scene_enqueue)
         expand_phase(s_stage, s_objs, s_lv, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size, k, rank,
-                     world);
+                     world, n_obj);
         front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0 + r + 1);
         stamp(gen);
     }
@@ -407,7 +434,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
     narrow_phase(s_objs, objs, cand, cand_cap, pairs, pair_cap, counters, n_cand);
     __syncthreads();
     stamp(gen + 1);
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = gen + 2; // number of stamps
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = n_stamps; // number of stamps
 }
 
 constexpr size_t kColSmemBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 128 KB
