@@ -346,10 +346,13 @@ def run_gpu_arm(args):
     pair_host = torch.empty((max(4 * n_pairs, 1 << 16), 4), dtype=torch.int32).pin_memory()
 
     def e2e_frame(i):
+        # both uploads are enqueued first (they run on the library's copy stream); body A's build + refit overlap
+        # body B's upload, which is why the builds are issued per tree here
         tree_a.set_positions_from_host_ptr(host_a.data_ptr())
         tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
-        ob.build_many([tree_a, tree_b])
+        tree_a.build()
         tree_a.refit(upload=False)
+        tree_b.build()
         tree_b.refit(upload=False)
         scene.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
         n, _ = scene.counts()  # D2H of the counters (sync)

@@ -59,6 +59,7 @@ struct oibvh_ctx
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr; // host->device uploads run here and overlap compute on `stream`
     uint64_t launches = 0;
     bool timing = false;
     bool capturing = false;
@@ -95,6 +96,10 @@ struct oibvh_tree
     uint32_t* sort_ctl = nullptr; // [hist: passes*radix][ticket: passes (padded to 64)][status: passes*tiles*radix]
     size_t sort_ctl_words = 0;
     uint32_t* done_counter = nullptr;
+    // upload pipeline: ev_uploaded = staging buffer filled (copy stream), ev_consumed = staging buffer packed (compute)
+    cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
+    bool consumed_recorded = false;
+    bool upload_pending = false; // staging buffer holds positions that have not been packed yet
 };
 
 struct oibvh_scene
@@ -184,6 +189,24 @@ void tree_free(oibvh_tree* t)
     cudaFree(t->vals_b);
     cudaFree(t->sort_ctl);
     cudaFree(t->done_counter);
+    if (t->ev_uploaded) cudaEventDestroy(t->ev_uploaded);
+    if (t->ev_consumed) cudaEventDestroy(t->ev_consumed);
+}
+
+// Positions uploaded by oibvh_tree_set_positions land in the staging buffer on the copy stream; the compute stream
+// picks them up (wait + widen to 16-byte records) lazily, right before the first operation that reads them, so the
+// upload overlaps everything enqueued in between.
+int tree_flush_upload(oibvh_tree* t)
+{
+    if (!t->upload_pending) return OIBVH_OK;
+    oibvh_ctx* ctx = t->ctx;
+    CU(cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0));
+    CU(launch_pack_positions(t->pos_stage, t->pos, t->V, ctx->stream));
+    count_launch(ctx);
+    CU(cudaEventRecord(t->ev_consumed, ctx->stream));
+    t->consumed_recorded = true;
+    t->upload_pending = false;
+    return OIBVH_OK;
 }
 
 int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6], oibvh_tree** out)
@@ -215,6 +238,8 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
         return rc;
     }
     cudaError_t e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t) * emit_counter_words(T), ctx->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_uploaded, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_consumed, cudaEventDisableTiming);
     if (e != cudaSuccess)
     {
         tree_free(t);
@@ -303,7 +328,8 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
         }
         c->own_stream = true;
     }
-    cudaError_t e = tree_emit_configure();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = tree_emit_configure();
     if (e == cudaSuccess) e = collide_configure(&c->collide_grid);
     if (e == cudaSuccess) e = coop_sort_configure();
     if (e != cudaSuccess)
@@ -332,6 +358,11 @@ extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
     {
         cudaEventDestroy(ev.a);
         cudaEventDestroy(ev.b);
+    }
+    if (ctx->copy_stream)
+    {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -524,6 +555,10 @@ extern "C" int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out)
     *out = nullptr;
     oibvh_ctx* ctx = other->ctx;
     DeviceGuard g(ctx->device);
+    {
+        int frc = tree_flush_upload(const_cast<oibvh_tree*>(other));
+        if (frc) return frc;
+    }
     oibvh_tree* t = nullptr;
     int rc = tree_alloc(ctx, other->V, other->T, other->mesh.v, &t);
     if (rc) return rc;
@@ -566,10 +601,31 @@ extern "C" int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_posi
 {
     REQUIRE(tree && host_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
-    CU(cudaMemcpyAsync(tree->pos_stage, host_positions, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyHostToDevice,
-                       tree->ctx->stream));
-    CU(launch_pack_positions(tree->pos_stage, tree->pos, tree->V, tree->ctx->stream));
-    count_launch(tree->ctx);
+    oibvh_ctx* ctx = tree->ctx;
+    const size_t bytes = sizeof(float) * 3 * (size_t)tree->V;
+    if (ctx->capturing)
+    {
+        // inside a graph capture everything stays on the one captured stream
+        CU(cudaMemcpyAsync(tree->pos_stage, host_positions, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    else
+    {
+        // The upload runs on the context's copy stream, so it overlaps whatever the compute stream is still doing
+        // (e.g. the previous tree's build); the compute stream only waits for it right before it needs the data.
+        // The staging buffer is reused: the copy first waits until its previous content has been packed.
+        if (tree->upload_pending)
+        {
+            // a previous upload was never consumed: it is simply superseded (same staging buffer, same stream order)
+        }
+        else if (tree->consumed_recorded)
+            CU(cudaStreamWaitEvent(ctx->copy_stream, tree->ev_consumed, 0));
+        CU(cudaMemcpyAsync(tree->pos_stage, host_positions, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(tree->ev_uploaded, ctx->copy_stream));
+        tree->upload_pending = true;
+        return OIBVH_OK;
+    }
+    CU(launch_pack_positions(tree->pos_stage, tree->pos, tree->V, ctx->stream));
+    count_launch(ctx);
     return OIBVH_OK;
 }
 
@@ -577,6 +633,7 @@ extern "C" int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const floa
 {
     REQUIRE(tree && dev_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
+    tree->upload_pending = false; // superseded
     CU(launch_pack_positions(dev_positions, tree->pos, tree->V, tree->ctx->stream));
     count_launch(tree->ctx);
     return OIBVH_OK;
@@ -586,6 +643,10 @@ extern "C" int oibvh_tree_transform(oibvh_tree* tree, const float M[16])
 {
     REQUIRE(tree && M, "NULL argument");
     DeviceGuard g(tree->ctx->device);
+    {
+        int rc = tree_flush_upload(tree);
+        if (rc) return rc;
+    }
     Mat4 m;
     memcpy(m.m, M, sizeof(float) * 16);
     CU(launch_transform(tree->pos, tree->V, m, tree->ctx->stream));
@@ -598,6 +659,10 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     REQUIRE(tree != nullptr, "tree is NULL");
     oibvh_ctx* ctx = tree->ctx;
     DeviceGuard g(ctx->device);
+    {
+        int rc = tree_flush_upload(tree);
+        if (rc) return rc;
+    }
     StageScope scope(ctx, OIBVH_STAGE_BUILD);
     cudaStream_t s = ctx->stream;
     const size_t radix = (size_t)1 << kRadixBits;
@@ -665,6 +730,11 @@ extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
         return OIBVH_OK;
     }
     DeviceGuard g(ctx->device);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        int rc = tree_flush_upload(trees[i]);
+        if (rc) return rc;
+    }
     StageScope scope(ctx, OIBVH_STAGE_BUILD);
     cudaStream_t s = ctx->stream;
     uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
@@ -714,6 +784,10 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
     REQUIRE(tree->built, "refit before build");
     oibvh_ctx* ctx = tree->ctx;
     DeviceGuard g(ctx->device);
+    {
+        int rc = tree_flush_upload(tree);
+        if (rc) return rc;
+    }
     StageScope scope(ctx, OIBVH_STAGE_REFIT);
     CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
                         ctx->stream));
@@ -769,6 +843,10 @@ extern "C" int oibvh_tree_download_positions(oibvh_tree* tree, float* host_posit
 {
     REQUIRE(tree && host_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
+    {
+        int rc = tree_flush_upload(tree);
+        if (rc) return rc;
+    }
     CU(launch_unpack_positions(tree->pos, tree->pos_stage, tree->V, tree->ctx->stream));
     count_launch(tree->ctx);
     CU(cudaMemcpyAsync(host_positions, tree->pos_stage, sizeof(float) * 3 * (size_t)tree->V, cudaMemcpyDeviceToHost,
@@ -897,7 +975,12 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     cudaStream_t st = ctx->stream;
     const uint32_t n_obj = (uint32_t)s->trees.size();
     uint32_t maxL = 0;
-    for (auto* t : s->trees) maxL = std::max(maxL, t->L);
+    for (auto* t : s->trees)
+    {
+        maxL = std::max(maxL, t->L);
+        int rc = tree_flush_upload(t); // the narrow phase reads the positions
+        if (rc) return rc;
+    }
     // One warp tests the 4^k descendant pairs of a node pair, 64 per iteration, so k = 3 costs one iteration per pair.
     // The fronts grow geometrically towards the leaves; the cheapest schedule (measured) makes EVERY round after the
     // first a 3-level round -- in particular the last, widest one -- and lets round 0 absorb the remainder.
