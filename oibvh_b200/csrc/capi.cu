@@ -116,10 +116,7 @@ struct oibvh_scene
     uint32_t* counters = nullptr;   // device, CTR_WORDS
     uint32_t* h_counters = nullptr; // pinned host mirror
     uint32_t rank = 0, world = 1;
-    uint32_t last_entry = 0, last_expand = 0, last_rounds = 0;
-    bool detect_pending = false;
-    uint32_t hint_front = 0, hint_cand = 0;
-    uint64_t enqueue_generation = 0;
+    uint32_t last_entry = 0, last_expand = 0, last_rounds = 0; // parameters of the last enqueued detection
 };
 
 namespace
@@ -1014,8 +1011,6 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     s->last_entry = entry_level;
     s->last_expand = requested_expand;
     s->last_rounds = rounds;
-    s->detect_pending = true;
-    s->enqueue_generation = ctx->generation;
     return OIBVH_OK;
 }
 
@@ -1045,7 +1040,6 @@ extern "C" int oibvh_scene_detect_async(oibvh_scene* scene, uint32_t entry_level
         CU(cudaMemsetAsync(scene->counters, 0, sizeof(uint32_t) * CTR_WORDS, ctx->stream));
         CU(cudaMemcpyAsync(scene->h_counters, scene->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost,
                            ctx->stream));
-        scene->detect_pending = true;
         scene->last_rounds = 0;
         return OIBVH_OK;
     }
@@ -1063,14 +1057,11 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         const uint32_t* h = scene->h_counters;
         uint32_t max_front = 0;
         for (uint32_t r = 0; r <= scene->last_rounds; r++) max_front = std::max(max_front, h[CTR_FRONT0 + r]);
-        scene->hint_front = max_front;
-        scene->hint_cand = h[CTR_CANDIDATES];
         if (h[CTR_OVERFLOW] & 8u) return fail(OIBVH_ERR_INTERNAL, "grid barrier timed out in the detection kernel");
         if (h[CTR_OVERFLOW] == 0)
         {
             if (n_pairs) *n_pairs = h[CTR_PAIRS];
             if (n_candidates) *n_candidates = h[CTR_CANDIDATES];
-            scene->detect_pending = false;
             return OIBVH_OK;
         }
         // a queue overflowed: grow (counts keep counting past the capacity, so they are lower bounds) and redo

@@ -51,27 +51,49 @@ __device__ __forceinline__ uint4 seed_entry(uint32_t n_obj, uint64_t p)
     return make_uint4(i, j, 0u, 0u);
 }
 
-__device__ void seed_phase(uint32_t n_obj, uint4* __restrict__ front, uint32_t front_cap,
-                           uint32_t* __restrict__ counters)
+// Many-body seeding = the top-level pass: one THREAD per object pair i < j tests the two root boxes, and only
+// overlapping pairs enter the front (warp-aggregated append). The reference seeds every pair on the host, O(n^2)
+// entries (src/cuda/scene.cu:192-223); here 4096 objects are 8.4 M cheap root tests and a front of a few thousand.
+__device__ void seed_phase(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* __restrict__ front,
+                           uint32_t front_cap, uint32_t* __restrict__ counters)
 {
     const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
+    const uint64_t rounded = (n_pairs + 31) & ~31ull;
+    const uint32_t lane = lane_id();
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += stride)
     {
-        // p -> (i, j), i < j, row-major over the strict upper triangle
-        const double nd = (double)n_obj;
-        uint32_t i = (uint32_t)floor((2.0 * nd - 1.0 - sqrt((2.0 * nd - 1.0) * (2.0 * nd - 1.0) - 8.0 * (double)p)) * 0.5);
-        // fix rounding of the closed form
-        while ((uint64_t)i * (2ull * n_obj - i - 1) / 2 > p) i--;
-        while ((uint64_t)(i + 1) * (2ull * n_obj - i - 2) / 2 <= p) i++;
-        const uint32_t j = (uint32_t)(p - (uint64_t)i * (2ull * n_obj - i - 1) / 2) + i + 1;
-        if (p < front_cap) front[p] = make_uint4(i, j, 0u, 0u);
+        bool hit = false;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (p < n_pairs)
+        {
+            e = seed_entry(n_obj, p);
+            const ObjDesc A = load_obj(objs, e.x), B = load_obj(objs, e.y);
+            hit = box_overlap(load_box(reinterpret_cast<const float2*>(A.nodes), 0),
+                              load_box(reinterpret_cast<const float2*>(B.nodes), 0));
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (mask)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(counters + CTR_FRONT0, (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit)
+            {
+                const uint32_t dst = base + __popc(mask & lanemask_lt());
+                if (dst < front_cap)
+                    front[dst] = e;
+                else
+                    atomicOr(counters + CTR_OVERFLOW, 1u);
+            }
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        counters[CTR_FRONT0] = (uint32_t)min(n_pairs, (uint64_t)0xffffffffu);
-        if (n_pairs > front_cap) atomicOr(counters + CTR_OVERFLOW, 1u);
-    }
+}
+
+// linear index of the object pair (i, j), i < j: the inverse of seed_entry (deterministic shard key)
+__device__ __forceinline__ uint32_t pair_linear(uint32_t n_obj, uint32_t i, uint32_t j)
+{
+    return (uint32_t)((uint64_t)i * (2ull * n_obj - i - 1) / 2) + (j - i - 1);
 }
 
 // Grid-wide barrier on a monotonically increasing arrival counter (zeroed with the counter block before the
@@ -209,11 +231,27 @@ __device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32
         // round 0: the seed rectangle is dealt round-robin to the shards
         if (world > 1 && round == 0)
         {
-            hit0 = hit0 && ((p + c0) % world) == rank;
-            hit1 = hit1 && ((p + c1) % world) == rank;
+            // keyed by the object pair's linear index, not by the (nondeterministic) slot of a seeded entry
+            const uint32_t key = computed_seeds ? p : pair_linear(n_obj, it.x, it.y);
+            hit0 = hit0 && ((key + c0) % world) == rank;
+            hit1 = hit1 && ((key + c1) % world) == rank;
         }
-        // nB is a power of two unless the rectangle is clamped by the end of the level
-        const uint32_t ia0 = c0 / nB, ib0 = c0 - ia0 * nB, ia1 = c1 / nB, ib1 = c1 - ia1 * nB;
+        // nB is a power of two unless the rectangle is clamped by the end of the level (warp-uniform either way)
+        uint32_t ia0, ib0, ia1, ib1;
+        if (nB == (1u << db))
+        {
+            ia0 = c0 >> db;
+            ib0 = c0 & (nB - 1);
+            ia1 = c1 >> db;
+            ib1 = c1 & (nB - 1);
+        }
+        else
+        {
+            ia0 = c0 / nB;
+            ib0 = c0 - ia0 * nB;
+            ia1 = c1 / nB;
+            ib1 = c1 - ia1 * nB;
+        }
         Box a0, b0, a1, b1;
         if (hit0)
         {
@@ -225,9 +263,10 @@ __device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32
             a1 = load_box(nodesA, baseA + ia1);
             b1 = load_box(nodesB, baseB + ib1);
         }
-        if (round == 0)
+        if (computed_seeds)
         {
-            // seeds are untested: prune object pairs whose root boxes are disjoint (loads overlap the ones above)
+            // computed root pairs are untested: prune object pairs whose root boxes are disjoint (seeded fronts
+            // were tested by the seeding pass; the loads overlap the ones above)
             const Box ra = load_box(nodesA, va.offset(la) + pa);
             const Box rb = load_box(nodesB, vb.offset(lb) + pb);
             if (!box_overlap(ra, rb)) continue; // warp-uniform
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
     }
     else
     {
-        seed_phase(n_obj, front0, front_cap, counters);
+        seed_phase(objs, n_obj, front0, front_cap, counters);
         front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0);
     }
     stamp(1);

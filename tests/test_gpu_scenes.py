@@ -130,3 +130,13 @@ def test_six_hundred_cubes(ctx, port):
     assert sc.getCandidateCount() == ncand
     assert np.array_equal(sc.canonical_pairs(), want)
     assert len({tuple(r) for r in want[:, :2].tolist()}) > 50
+    # shards of a seeded (many-body) scene partition the pair set too
+    parts = []
+    for rank in range(3):
+        sc.set_shard(rank, 3)
+        sc.detectCollision(ob.DeviceType.GPU0, 4, 0)
+        parts.append(sc.canonical_pairs())
+    allp = np.concatenate(parts)
+    assert len(allp) == len(want)
+    allp = allp[np.lexsort((allp[:, 3], allp[:, 2], allp[:, 1], allp[:, 0]))]
+    assert np.array_equal(allp, want)
