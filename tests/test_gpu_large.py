@@ -106,3 +106,27 @@ def test_four_million_properties(ctx):
     t.refit(upload=False)
     n2 = t.m_aabbTree
     check_tree_properties(n2, d["faces"], d["perm"], t.sorted_keys(), pos2, faces)
+
+
+def test_sixteen_million_terrain_vs_million_body(ctx, port):
+    """configs[4] at full size: 16.8 M-triangle terrain (L = 25 levels, streaming onesweep sort) against a
+    2^20-triangle body pressed into it; the CPU restatement needs ~2 s for this"""
+    tpos, tfaces = meshgen.terrain(2897, 2897, height=0.3, size=(8.0, 8.0))
+    bpos, bfaces = meshgen.blob(1024, 512, seed=5, radius=1.5, center=(0.2, 0.9, -0.3))
+    terrain = ob.OibvhTree(ob.Mesh(tpos, tfaces), ctx=ctx)
+    body = ob.OibvhTree(ob.Mesh(bpos, bfaces), ctx=ctx)
+    terrain.build()
+    body.build()
+    ot, obody = port.build(tpos, tfaces), port.build(bpos, bfaces)
+    d = terrain.download()
+    assert np.array_equal(d["perm"], ot["perm"])
+    assert_bit_equal(d["nodes"], ot["nodes"], "16.8M build")
+    sc = ob.Scene(ctx)
+    sc.addOibvhTree(terrain)
+    sc.addOibvhTree(body)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 0)
+    pp, nc = port.detect([(ot["nodes"], ot["faces"], tpos), (obody["nodes"], obody["faces"], bpos)])
+    assert sc.getCandidateCount() == nc
+    assert np.array_equal(sc.canonical_pairs(), oracle.canonical_pairs(pp, [ot["perm"], obody["perm"]]))
+    assert len(pp) > 5000
+    terrain.close()
