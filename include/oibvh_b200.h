@@ -122,12 +122,21 @@ int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const float* dev_posi
 int oibvh_tree_transform(oibvh_tree* tree, const float M[16]);
 /* OibvhTree::build (src/cuda/oibvhTree.cu:237-388): Morton keys, stable sort, implicit-layout AABB reduction */
 int oibvh_tree_build(oibvh_tree* tree);
-/* Build several trees of the same context together (extension; the reference builds one tree per call): the keys of
- * all trees are sorted by ONE cooperative launch, which costs the grid barriers of a single sort. Falls back to
- * consecutive oibvh_tree_build calls when the trees do not fit one launch. Results are identical to separate builds. */
+/* Build several trees of the same context together (extension; the reference builds one tree per call, one
+ * OibvhTree::build per object of a many-body scene). Results are identical to separate builds.
+ *  - trees of up to 4096 triangles: ALL of them in one launch, one thread block per tree;
+ *  - larger trees: the keys of 2..4 trees are sorted by ONE cooperative launch (the grid barriers of a single sort);
+ *    otherwise consecutive oibvh_tree_build calls.
+ * The device table naming the trees is kept while the same list is passed again (no upload on later calls; only such
+ * repeat calls may be captured into a graph). */
 int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n);
 /* OibvhTree::refit (src/cuda/oibvhTree.cu:193-235) on the positions currently on the device */
 int oibvh_tree_refit(oibvh_tree* tree);
+/* the per-object refit loop of a many-body frame: small trees in one launch, larger ones one launch each */
+int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n);
+/* oibvh_tree_transform for n trees in one launch; mats = n column-major 4x4 matrices (host / device memory) */
+int oibvh_tree_transform_many(oibvh_tree* const* trees, uint32_t n, const float* host_mats);
+int oibvh_tree_transform_many_from_device(oibvh_tree* const* trees, uint32_t n, const float* dev_mats);
 /* getPrimCount / vertex count / oibvh_get_size(T) / getDepth() = ilog2(N)  (oibvhTree.cu:45-53) */
 int oibvh_tree_get_info(const oibvh_tree* tree, uint32_t* T, uint32_t* V, uint32_t* N, uint32_t* depth);
 int oibvh_tree_is_built(const oibvh_tree* tree, int* built);

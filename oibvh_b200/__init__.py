@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboibvh_b200.so")
+# OIBVH_B200_LIB selects another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("OIBVH_B200_LIB") or os.path.join(_HERE, "liboibvh_b200.so")
 
 STAGES = ("build", "refit", "broad", "narrow")
 
@@ -70,6 +71,9 @@ _SIGNATURES = {
     "oibvh_tree_transform": (C.c_int, [_vp, _f32p]),
     "oibvh_tree_build": (C.c_int, [_vp]),
     "oibvh_tree_build_many": (C.c_int, [C.POINTER(_vp), _u32]),
+    "oibvh_tree_refit_many": (C.c_int, [C.POINTER(_vp), _u32]),
+    "oibvh_tree_transform_many": (C.c_int, [C.POINTER(_vp), _u32, _f32p]),
+    "oibvh_tree_transform_many_from_device": (C.c_int, [C.POINTER(_vp), _u32, _vp]),
     "oibvh_tree_refit": (C.c_int, [_vp]),
     "oibvh_tree_get_info": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
     "oibvh_tree_is_built": (C.c_int, [_vp, C.POINTER(C.c_int)]),
@@ -473,12 +477,49 @@ class OibvhTree:
         return a.value, b.value, c.value
 
 
+class TreeBatch:
+    """a fixed list of trees with its handle array prepared once: pass it to build_many / refit_many /
+    transform_many every frame (a many-body scene has thousands of trees; rebuilding the array costs more than the
+    launch)"""
+
+    def __init__(self, trees):
+        self.trees = list(trees)
+        self._arr = (_vp * len(self.trees))(*[t._h for t in self.trees])
+
+    def __len__(self):
+        return len(self.trees)
+
+    def __iter__(self):
+        return iter(self.trees)
+
+
+def _handles(trees):
+    if isinstance(trees, TreeBatch):
+        return trees._arr
+    return (_vp * len(trees))(*[t._h for t in trees])
+
+
 def build_many(trees):
-    """build several trees together: one cooperative launch sorts all their keys (oibvh_tree_build_many)"""
-    arr = (_vp * len(trees))(*[t._h for t in trees])
-    _check(_lib.oibvh_tree_build_many(arr, len(trees)))
+    """build several trees together (oibvh_tree_build_many): every tree of <= 4096 triangles in one launch, the keys
+    of 2..4 larger trees in one cooperative sort launch"""
+    _check(_lib.oibvh_tree_build_many(_handles(trees), len(trees)))
     for t in trees:
         t.m_buildDone = True
+
+
+def refit_many(trees):
+    """refit several trees on their device-resident positions (oibvh_tree_refit_many): small trees in one launch"""
+    _check(_lib.oibvh_tree_refit_many(_handles(trees), len(trees)))
+
+
+def transform_many(trees, mats, device_ptr=None):
+    """one rigid transform per tree in ONE launch (oibvh_tree_transform_many). mats: (n, 4, 4) glm-order matrices
+    (mats[i][column][row], as Mesh.transform_matrix_*) on the host, or device_ptr = address of n x 16 floats."""
+    if device_ptr is not None:
+        _check(_lib.oibvh_tree_transform_many_from_device(_handles(trees), len(trees), _vp(device_ptr)))
+        return
+    m = np.ascontiguousarray(mats, np.float32).reshape(len(trees), 16)
+    _check(_lib.oibvh_tree_transform_many(_handles(trees), len(trees), m.ctypes.data_as(_f32p)))
 
 
 # =====================================================================================================

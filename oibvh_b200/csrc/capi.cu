@@ -68,6 +68,18 @@ struct oibvh_ctx
     uint64_t generation = 0; // bumped whenever device buffers referenced by enqueued work are reallocated
     std::vector<StageEvent> events;
     float stage_ms[OIBVH_STAGE_COUNT] = {0, 0, 0, 0};
+    // device tables of the *_many entry points, kept while the same list of trees is passed again (per-frame calls
+    // then upload nothing and can be captured into a graph)
+    struct BatchTable
+    {
+        std::vector<oibvh_tree*> key;
+        void* dev = nullptr;
+        size_t cap_bytes = 0;
+        uint32_t total_blocks = 0;
+    };
+    BatchTable small_table, xform_table;
+    float* d_mats = nullptr;
+    size_t d_mats_cap = 0;
 };
 
 struct oibvh_graph
@@ -96,6 +108,9 @@ struct oibvh_tree
     uint32_t* sort_ctl = nullptr; // [hist: passes*radix][ticket: passes (padded to 64)][status: passes*tiles*radix]
     size_t sort_ctl_words = 0;
     uint32_t* done_counter = nullptr;
+    // T <= kSmallTreeMax: built / refitted by one CTA (small_tree_kernel); no second sort buffers, no control blocks
+    bool small = false;
+    SmallTreeDesc* d_small = nullptr; // this tree's entry for single-tree launches
     // upload pipeline: ev_uploaded = staging buffer filled (copy stream), ev_consumed = staging buffer packed (compute)
     cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
     bool consumed_recorded = false;
@@ -184,6 +199,7 @@ void tree_free(oibvh_tree* t)
     cudaFree(t->keys_b);
     cudaFree(t->vals_a);
     cudaFree(t->vals_b);
+    cudaFree(t->d_small);
     cudaFree(t->sort_ctl);
     cudaFree(t->done_counter);
     if (t->ev_uploaded) cudaEventDestroy(t->ev_uploaded);
@@ -206,6 +222,21 @@ int tree_flush_upload(oibvh_tree* t)
     return OIBVH_OK;
 }
 
+SmallTreeDesc small_desc_of(const oibvh_tree* t)
+{
+    SmallTreeDesc h;
+    h.faces_in = t->faces_in;
+    h.pos = t->pos;
+    h.faces = t->faces;
+    h.nodes = t->nodes;
+    h.keys = t->keys_a;
+    h.perm = t->vals_a;
+    h.mesh = t->mesh;
+    h.T = t->T;
+    h.L = t->L;
+    return h;
+}
+
 int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6], oibvh_tree** out)
 {
     oibvh_tree* t = new (std::nothrow) oibvh_tree;
@@ -220,21 +251,31 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
     const size_t radix = (size_t)1 << kRadixBits;
     t->sort_ctl_words = std::max(kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix,
                                  coop_sort_ctl_words());
+    t->small = T <= kSmallTreeMax;
     int rc = OIBVH_OK;
     // round the index buffers up to whole 16-byte groups so that 128-bit accesses of the last group stay in bounds
     const size_t T4 = ((size_t)T + 3) / 4 * 4;
     if ((rc = dev_alloc(&t->pos, (size_t)V)) || (rc = dev_alloc(&t->pos_stage, (size_t)V * 3)) ||
         (rc = dev_alloc(&t->faces_in, T4)) ||
         (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
-        (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
-        (rc = dev_alloc(&t->vals_b, T4)) || (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
-        (rc = dev_alloc(&t->done_counter, emit_counter_words(T))))
+        (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
+        (t->small ? (rc = dev_alloc(&t->d_small, 1))
+                  : ((rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_b, T4)) ||
+                     (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
+                     (rc = dev_alloc(&t->done_counter, emit_counter_words(T))))))
     {
         tree_free(t);
         delete t;
         return rc;
     }
-    cudaError_t e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t) * emit_counter_words(T), ctx->stream);
+    cudaError_t e = cudaSuccess;
+    if (t->small)
+    {
+        const SmallTreeDesc h = small_desc_of(t);
+        e = cudaMemcpyAsync(t->d_small, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream); // pageable: staged on return
+    }
+    else
+        e = cudaMemsetAsync(t->done_counter, 0, sizeof(uint32_t) * emit_counter_words(T), ctx->stream);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_uploaded, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_consumed, cudaEventDisableTiming);
     if (e != cudaSuccess)
@@ -362,6 +403,9 @@ extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
         cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->small_table.dev);
+    cudaFree(ctx->xform_table.dev);
+    cudaFree(ctx->d_mats);
     delete ctx;
     return OIBVH_OK;
 }
@@ -589,6 +633,8 @@ extern "C" int oibvh_tree_destroy(oibvh_tree* tree)
     if (!tree) return OIBVH_OK;
     DeviceGuard g(tree->ctx->device);
     cudaStreamSynchronize(tree->ctx->stream);
+    tree->ctx->small_table.key.clear(); // cached *_many tables may name this tree
+    tree->ctx->xform_table.key.clear();
     tree_free(tree);
     delete tree;
     return OIBVH_OK;
@@ -662,6 +708,14 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     }
     StageScope scope(ctx, OIBVH_STAGE_BUILD);
     cudaStream_t s = ctx->stream;
+    if (tree->small)
+    {
+        // keys, sort, gather, leaves and all levels by one CTA
+        CU(launch_small_trees(true, tree->d_small, 1, s));
+        count_launch(ctx);
+        tree->built = true;
+        return OIBVH_OK;
+    }
     const size_t radix = (size_t)1 << kRadixBits;
     uint32_t* hist = tree->sort_ctl;
     uint32_t* ticket = tree->sort_ctl + kRadixPasses * radix;
@@ -703,10 +757,80 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     return OIBVH_OK;
 }
 
+// Device table for a list of trees, cached on the context while the same list is passed again.
+static int batch_table_upload(oibvh_ctx* ctx, oibvh_ctx::BatchTable& tab, const std::vector<oibvh_tree*>& list,
+                              const void* host, size_t bytes)
+{
+    REQUIRE(!ctx->capturing, "call the *_many entry point once with this list of trees before capturing it");
+    tab.key.clear();
+    ctx->generation++; // graphs captured with the previous table must not replay
+    if (bytes > tab.cap_bytes)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tab.dev);
+        tab.dev = nullptr;
+        tab.cap_bytes = 0;
+        CU(cudaMalloc(&tab.dev, bytes));
+        tab.cap_bytes = bytes;
+    }
+    CU(cudaMemcpyAsync(tab.dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // the host copy goes out of scope
+    tab.key = list;
+    return OIBVH_OK;
+}
+
+static int small_batch_table(oibvh_ctx* ctx, const std::vector<oibvh_tree*>& list, const SmallTreeDesc** out)
+{
+    auto& tab = ctx->small_table;
+    if (!(tab.dev && tab.key == list))
+    {
+        std::vector<SmallTreeDesc> h(list.size());
+        for (size_t i = 0; i < list.size(); i++) h[i] = small_desc_of(list[i]);
+        int rc = batch_table_upload(ctx, tab, list, h.data(), sizeof(SmallTreeDesc) * h.size());
+        if (rc) return rc;
+    }
+    *out = static_cast<const SmallTreeDesc*>(tab.dev);
+    return OIBVH_OK;
+}
+
+static int build_large_many(oibvh_tree* const* trees, uint32_t n);
+
 extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
 {
     REQUIRE(trees != nullptr && n >= 1, "no trees");
-    for (uint32_t i = 0; i < n; i++) REQUIRE(trees[i] != nullptr, "NULL tree");
+    oibvh_ctx* ctx = trees[0] ? trees[0]->ctx : nullptr;
+    std::vector<oibvh_tree*> small_list, large_list;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        REQUIRE(trees[i] != nullptr, "NULL tree");
+        REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
+        (trees[i]->small ? small_list : large_list).push_back(trees[i]);
+    }
+    if (small_list.size() == 1)
+    {
+        int rc = oibvh_tree_build(small_list[0]);
+        if (rc) return rc;
+    }
+    else if (!small_list.empty())
+    {
+        // every small tree of the list in ONE launch, one CTA each
+        DeviceGuard g(ctx->device);
+        const SmallTreeDesc* table = nullptr;
+        int rc = small_batch_table(ctx, small_list, &table);
+        if (rc) return rc;
+        for (auto* t : small_list)
+            if ((rc = tree_flush_upload(t))) return rc;
+        StageScope scope(ctx, OIBVH_STAGE_BUILD);
+        CU(launch_small_trees(true, table, (uint32_t)small_list.size(), ctx->stream));
+        count_launch(ctx);
+        for (auto* t : small_list) t->built = true;
+    }
+    if (large_list.empty()) return OIBVH_OK;
+    return build_large_many(large_list.data(), (uint32_t)large_list.size());
+}
+
+static int build_large_many(oibvh_tree* const* trees, uint32_t n)
+{
     oibvh_ctx* ctx = trees[0]->ctx;
     uint64_t total = 0;
     bool batch = n >= 2 && n <= 4;
@@ -786,10 +910,112 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
         if (rc) return rc;
     }
     StageScope scope(ctx, OIBVH_STAGE_REFIT);
-    CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
-                        ctx->stream));
+    if (tree->small)
+        CU(launch_small_trees(false, tree->d_small, 1, ctx->stream));
+    else
+        CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
+                            ctx->stream));
     count_launch(ctx);
     return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
+{
+    REQUIRE(trees != nullptr && n >= 1, "no trees");
+    oibvh_ctx* ctx = trees[0] ? trees[0]->ctx : nullptr;
+    std::vector<oibvh_tree*> small_list;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        REQUIRE(trees[i] != nullptr, "NULL tree");
+        REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
+        REQUIRE(trees[i]->built, "refit before build");
+        if (trees[i]->small) small_list.push_back(trees[i]);
+    }
+    DeviceGuard g(ctx->device);
+    if (small_list.size() >= 2)
+    {
+        const SmallTreeDesc* table = nullptr;
+        int rc = small_batch_table(ctx, small_list, &table);
+        if (rc) return rc;
+        for (auto* t : small_list)
+            if ((rc = tree_flush_upload(t))) return rc;
+        StageScope scope(ctx, OIBVH_STAGE_REFIT);
+        CU(launch_small_trees(false, table, (uint32_t)small_list.size(), ctx->stream));
+        count_launch(ctx);
+    }
+    for (uint32_t i = 0; i < n; i++)
+        if (!trees[i]->small || small_list.size() < 2)
+        {
+            int rc = oibvh_tree_refit(trees[i]);
+            if (rc) return rc;
+        }
+    return OIBVH_OK;
+}
+
+static int transform_many_impl(oibvh_tree* const* trees, uint32_t n, const float* mats, bool from_device)
+{
+    REQUIRE(trees != nullptr && n >= 1 && mats != nullptr, "NULL argument");
+    oibvh_ctx* ctx = trees[0] ? trees[0]->ctx : nullptr;
+    std::vector<oibvh_tree*> list(trees, trees + n);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        REQUIRE(trees[i] != nullptr, "NULL tree");
+        REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
+    }
+    DeviceGuard g(ctx->device);
+    auto& tab = ctx->xform_table;
+    if (!(tab.dev && tab.key == list))
+    {
+        std::vector<XformDesc> h(n);
+        uint64_t blocks = 0;
+        for (uint32_t i = 0; i < n; i++)
+        {
+            h[i].pos = trees[i]->pos;
+            h[i].V = trees[i]->V;
+            h[i].block0 = (uint32_t)blocks;
+            blocks += (trees[i]->V + 255) / 256;
+        }
+        REQUIRE(blocks < 0x7fffffffull, "too many vertices for one transform launch");
+        int rc = batch_table_upload(ctx, tab, list, h.data(), sizeof(XformDesc) * n);
+        if (rc) return rc;
+        tab.total_blocks = (uint32_t)blocks;
+    }
+    for (uint32_t i = 0; i < n; i++)
+    {
+        int rc = tree_flush_upload(trees[i]);
+        if (rc) return rc;
+    }
+    const float* d_mats = mats;
+    if (!from_device)
+    {
+        const size_t bytes = sizeof(float) * 16 * (size_t)n;
+        if (bytes > ctx->d_mats_cap)
+        {
+            REQUIRE(!ctx->capturing, "call oibvh_tree_transform_many once with this many trees before capturing it");
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_mats);
+            ctx->d_mats = nullptr;
+            ctx->d_mats_cap = 0;
+            ctx->generation++;
+            CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mats), bytes));
+            ctx->d_mats_cap = bytes;
+        }
+        CU(cudaMemcpyAsync(ctx->d_mats, mats, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_mats = ctx->d_mats;
+    }
+    CU(launch_transform_many(static_cast<const XformDesc*>(tab.dev), n, tab.total_blocks, d_mats, ctx->stream));
+    count_launch(ctx);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_transform_many(oibvh_tree* const* trees, uint32_t n, const float* host_mats)
+{
+    return transform_many_impl(trees, n, host_mats, false);
+}
+
+extern "C" int oibvh_tree_transform_many_from_device(oibvh_tree* const* trees, uint32_t n, const float* dev_mats)
+{
+    return transform_many_impl(trees, n, dev_mats, true);
 }
 
 extern "C" int oibvh_tree_get_info(const oibvh_tree* tree, uint32_t* T, uint32_t* V, uint32_t* N, uint32_t* depth)

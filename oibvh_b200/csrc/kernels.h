@@ -51,6 +51,29 @@ cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t*
                              const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s);
 cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream_t s);
 
+// ---- many small trees per launch (many-body scenes) ----
+constexpr uint32_t kSmallTreeMax = 4096; // one CTA sorts and reduces the whole tree in shared memory / L2
+struct SmallTreeDesc
+{
+    const uint4* faces_in; // T x (i0, i1, i2, 0), input order
+    const float4* pos;
+    uint32_t* faces; // T x 3, Morton order (written by a build, read by a refit)
+    float* nodes;
+    uint32_t* keys; // sorted keys / permutation, written by a build
+    uint32_t* perm;
+    MeshAabb mesh;
+    uint32_t T, L;
+};
+cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n, cudaStream_t s);
+struct XformDesc
+{
+    float4* pos;
+    uint32_t V;
+    uint32_t block0; // first 256-vertex block of this tree in the launch
+};
+cudaError_t launch_transform_many(const XformDesc* descs, uint32_t n, uint32_t total_blocks, const float* mats,
+                                  cudaStream_t s);
+
 // ---- collision ----
 // one entry of the device object table (Scene::m_aabbOffsets/m_primOffsets/m_vertexOffsets/m_primCounts of the
 // reference, src/cuda/scene.cu:95-129, become direct views of each tree's device buffers)

@@ -781,6 +781,122 @@ __global__ void __launch_bounds__(256) transform_kernel(float4* __restrict__ pos
 }
 
 // =================================================================================================
+// Small trees (T <= kSmallTreeMax): keys, stable sort, face gather, leaves and every inner level by ONE CTA; a launch
+// takes a table of trees (one CTA each), so a many-body scene of thousands of small objects builds or refits in a
+// single launch instead of three (one) launches per object. Same results as the large-tree path: the sort key is
+// (Morton key, input index), i.e. thrust::stable_sort_by_key order (src/cuda/oibvhTree.cu:295-296); a parent with a
+// dropped right child copies its left child.
+// =================================================================================================
+constexpr int kSmallThreads = 128;
+
+template <bool BUILD>
+__global__ void __launch_bounds__(kSmallThreads) small_tree_kernel(const SmallTreeDesc* __restrict__ descs)
+{
+    __shared__ unsigned long long s_kv[BUILD ? kSmallTreeMax : 1];
+    const SmallTreeDesc d = descs[blockIdx.x];
+    const uint32_t T = d.T, L = d.L, tid = threadIdx.x;
+    float2* nodes = reinterpret_cast<float2*>(d.nodes);
+    const uint32_t leaf_off = level_offset(T, L, L);
+    if (BUILD)
+    {
+        const uint32_t P = 1u << L; // padded to a power of two; padding sorts last
+        for (uint32_t i = tid; i < P; i += kSmallThreads)
+        {
+            unsigned long long kv = ~0ull;
+            if (i < T)
+            {
+                const uint4 f = d.faces_in[i];
+                const uint32_t key = morton_of_box(box_of(d.pos[f.x], d.pos[f.y], d.pos[f.z]), d.mesh);
+                kv = ((unsigned long long)key << 32) | i;
+            }
+            s_kv[i] = kv;
+        }
+        __syncthreads();
+        // bitonic network on the 64-bit composites (all distinct, so the result is the stable order)
+        for (uint32_t k = 2; k <= P; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1)
+            {
+                for (uint32_t t = tid; t < (P >> 1); t += kSmallThreads)
+                {
+                    const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const uint32_t hi = lo | j;
+                    const unsigned long long a = s_kv[lo], b = s_kv[hi];
+                    if ((a > b) == ((lo & k) == 0))
+                    {
+                        s_kv[lo] = b;
+                        s_kv[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        for (uint32_t i = tid; i < T; i += kSmallThreads)
+        {
+            const unsigned long long kv = s_kv[i];
+            const uint32_t id = (uint32_t)kv;
+            d.keys[i] = (uint32_t)(kv >> 32);
+            d.perm[i] = id;
+            const uint4 f = d.faces_in[id];
+            d.faces[3 * i] = f.x;
+            d.faces[3 * i + 1] = f.y;
+            d.faces[3 * i + 2] = f.z;
+            store_box(nodes, leaf_off + i, box_of(d.pos[f.x], d.pos[f.y], d.pos[f.z]));
+        }
+    }
+    else
+    {
+        for (uint32_t i = tid; i < T; i += kSmallThreads)
+        {
+            const uint32_t a = d.faces[3 * i], b = d.faces[3 * i + 1], c = d.faces[3 * i + 2];
+            store_box(nodes, leaf_off + i, box_of(d.pos[a], d.pos[b], d.pos[c]));
+        }
+    }
+    // inner levels, bottom-up; the children were written by this CTA (read back through L2)
+    uint32_t child_off = leaf_off, child_cnt = T;
+    for (int l = (int)L - 1; l >= 0; l--)
+    {
+        __syncthreads();
+        const uint32_t cnt = level_count(T, L, (uint32_t)l), off = level_offset(T, L, (uint32_t)l);
+        for (uint32_t p = tid; p < cnt; p += kSmallThreads)
+        {
+            Box b = load_box_cg(nodes, child_off + 2 * p);
+            if (2 * p + 1 < child_cnt) b = box_merge(b, load_box_cg(nodes, child_off + 2 * p + 1));
+            store_box(nodes, off + p, b);
+        }
+        child_off = off;
+        child_cnt = cnt;
+    }
+}
+
+// Rigid transforms of many trees in one launch: block -> (tree, 256-vertex chunk) through the block prefix table.
+__global__ void __launch_bounds__(256) transform_many_kernel(const XformDesc* __restrict__ descs, uint32_t n,
+                                                             const float* __restrict__ mats)
+{
+    uint32_t lo = 0, hi = n; // largest i with descs[i].block0 <= blockIdx.x
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (descs[mid].block0 <= blockIdx.x)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const XformDesc d = descs[lo];
+    const uint32_t i = (blockIdx.x - d.block0) * 256 + threadIdx.x;
+    if (i >= d.V) return;
+    const float* M = mats + 16ull * lo;
+    const float4 p = d.pos[i];
+    float r[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const float add0 = __fadd_rn(__fmul_rn(M[0 + k], p.x), __fmul_rn(M[4 + k], p.y));
+        const float add1 = __fadd_rn(__fmul_rn(M[8 + k], p.z), __fmul_rn(M[12 + k], 1.0f));
+        r[k] = __fadd_rn(add0, add1);
+    }
+    d.pos[i] = make_float4(r[0], r[1], r[2], 1.0f);
+}
+
+// =================================================================================================
 // Launchers
 // =================================================================================================
 cudaError_t launch_pack_positions(const float* xyz, float4* pos4, uint32_t V, cudaStream_t s)
@@ -881,4 +997,21 @@ cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream
     return cudaGetLastError();
 }
 
+cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    if (build)
+        small_tree_kernel<true><<<n, kSmallThreads, 0, s>>>(descs);
+    else
+        small_tree_kernel<false><<<n, kSmallThreads, 0, s>>>(descs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform_many(const XformDesc* descs, uint32_t n, uint32_t total_blocks, const float* mats,
+                                  cudaStream_t s)
+{
+    if (n == 0 || total_blocks == 0) return cudaSuccess;
+    transform_many_kernel<<<total_blocks, 256, 0, s>>>(descs, n, mats);
+    return cudaGetLastError();
+}
 } // namespace oibvh

@@ -9,7 +9,7 @@ from oibvh_b200 import meshgen
 pytestmark = pytest.mark.gpu
 
 # edge sizes: T=2 (minimum), odd, 2^k, 2^k+-1, one chunk (1024) +-1, several chunks, vl = P-1 (T = 2^k + 1)
-SIZES = [2, 3, 4, 5, 6, 7, 12, 13, 31, 33, 100, 255, 256, 257, 1000, 1023, 1024, 1025, 2049, 4097, 5000, 20480, 34816]
+SIZES = [2, 3, 4, 5, 6, 7, 12, 13, 31, 33, 100, 255, 256, 257, 1000, 1023, 1024, 1025, 2049, 4095, 4096, 4097, 5000, 20480, 34816]
 
 
 def check_build(ctx, port, pos, faces, aabb=None):
@@ -166,3 +166,59 @@ def test_build_many_equals_separate_builds(ctx, port):
         assert_bit_equal(d["nodes"], w["nodes"], "build_many nodes")
     ob.build_many(trees[:1])  # n = 1 falls back to a plain build
     assert_bit_equal(trees[0].download()["nodes"], wants[0]["nodes"], "build_many(1)")
+
+
+def test_many_small_trees_in_one_launch(ctx, port):
+    """many-body path: trees of <= 4096 triangles build / refit one CTA each, all in one launch; mixed with large
+    trees in the same call. Results must equal the oracle tree by tree."""
+    rng = np.random.default_rng(11)
+    specs = []
+    for i in range(40):
+        kind = i % 5
+        if kind == 0:
+            pos, faces = meshgen.cube()
+        elif kind == 1:
+            pos, faces = meshgen.icosphere(2)
+        elif kind == 2:
+            pos, faces = meshgen.icosphere(3)
+        elif kind == 3:
+            pos, faces = meshgen.blob(64, 40, seed=i)
+            faces = faces[: int(rng.integers(2, 4097))]
+        else:
+            pos, faces = meshgen.blob(64, 40, seed=i)
+            faces = faces[:4096]
+        specs.append((pos, meshgen.shuffle_faces(np.ascontiguousarray(faces), seed=i)))
+    specs.append((meshgen.blob(120, 90, seed=77)[0], meshgen.shuffle_faces(meshgen.blob(120, 90, seed=77)[1])))  # large
+    specs.append((meshgen.icosphere(4)[0], meshgen.shuffle_faces(meshgen.icosphere(4)[1])))  # large
+    meshes = [ob.Mesh(p, f) for p, f in specs]
+    trees = [ob.OibvhTree(m, ctx=ctx) for m in meshes]
+    wants = [port.build(p, f, m.m_aabb) for (p, f), m in zip(specs, meshes)]
+    before = ctx.launch_count()
+    ob.build_many(trees)
+    launches = ctx.launch_count() - before
+    assert launches <= 1 + 3 + 3, f"40 small trees must share one launch (got {launches} launches)"
+    for t, w in zip(trees, wants):
+        d = t.download()
+        assert np.array_equal(t.sorted_keys(), w["keys"])
+        assert np.array_equal(d["perm"], w["perm"])
+        assert np.array_equal(d["faces"], w["faces"])
+        assert_bit_equal(d["nodes"], w["nodes"], "build_many (small) nodes")
+    # one rigid transform per tree in one launch, then the refit of all of them
+    mats = np.stack([m.transform_matrix_rotate((0.3, 1.0, 0.2), 10.0 + i) if i % 2 else
+                     m.transform_matrix_translate((0.1 * i, -0.2, 0.05 * i)) for i, m in enumerate(meshes)])
+    before = ctx.launch_count()
+    ob.transform_many(trees, mats)
+    ob.refit_many(trees)
+    assert ctx.launch_count() - before == 1 + 1 + 2
+    for i, (t, w) in enumerate(zip(trees, wants)):
+        pos2 = port.transform_positions(specs[i][0], mats[i])
+        assert_bit_equal(t.m_positions, pos2, f"transform_many tree {i}")
+        assert_bit_equal(t.download()["nodes"], port.refit(pos2, w["faces"]), f"refit_many tree {i}")
+    # same list again: cached device tables, same results; then a different list
+    ob.refit_many(trees)
+    ob.refit_many(trees[5:20])
+    ob.build_many(trees[:7])
+    for t, m, (p, f), M in list(zip(trees, meshes, specs, mats))[:7]:
+        w2 = port.build(port.transform_positions(p, M), f, m.m_aabb)  # keys from the moved vertices, original mesh box
+        assert np.array_equal(t.download()["perm"], w2["perm"])
+        assert_bit_equal(t.download()["nodes"], w2["nodes"], "rebuild after the transform")
