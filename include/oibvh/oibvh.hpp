@@ -311,6 +311,31 @@ public:
     }
     oibvh_tree* handle() const { return m_handle; }
 
+    // Many-body extensions (the reference loops over its objects, one build / refit call each): every tree of up to
+    // 4096 triangles is processed by one thread block of ONE launch. Results equal the per-tree calls.
+    static void buildMany(const std::vector<std::shared_ptr<OibvhTree>>& trees)
+    {
+        std::vector<oibvh_tree*> h = handles(trees);
+        oibvh_detail::check(oibvh_tree_build_many(h.data(), (uint32_t)h.size()));
+        for (auto& t : trees) t->m_buildDone = true;
+    }
+    // refit on the positions currently on the device (after transformMany / oibvh_tree_transform)
+    static void refitManyOnDevice(const std::vector<std::shared_ptr<OibvhTree>>& trees)
+    {
+        std::vector<oibvh_tree*> h = handles(trees);
+        oibvh_detail::check(oibvh_tree_refit_many(h.data(), (uint32_t)h.size()));
+    }
+    // Mesh::transform of every object on its device-resident vertices, one matrix per tree
+    static void transformMany(const std::vector<std::shared_ptr<OibvhTree>>& trees,
+                              const std::vector<oibvh_math::mat4>& mats)
+    {
+        if (mats.size() != trees.size()) throw std::runtime_error("transformMany: one matrix per tree");
+        static_assert(sizeof(oibvh_math::mat4) == 64, "mat4 is 16 packed floats, column-major");
+        std::vector<oibvh_tree*> h = handles(trees);
+        oibvh_detail::check(oibvh_tree_transform_many(h.data(), (uint32_t)h.size(),
+                                                      reinterpret_cast<const float*>(mats.data())));
+    }
+
     std::vector<aabb_box_t> m_aabbTree;          // N nodes, real-index order (after syncHost)
     std::vector<oibvh_math::uvec3> m_faces;      // Morton-sorted faces (after syncHost)
     std::vector<oibvh_math::vec3> m_positions;   // (after syncHost)
@@ -318,6 +343,13 @@ public:
     bool m_buildDone;
 
 private:
+    static std::vector<oibvh_tree*> handles(const std::vector<std::shared_ptr<OibvhTree>>& trees)
+    {
+        std::vector<oibvh_tree*> h;
+        h.reserve(trees.size());
+        for (auto& t : trees) h.push_back(t->m_handle);
+        return h;
+    }
     std::vector<float> packedPositions() const
     {
         std::vector<float> pos(3 * (size_t)m_mesh->m_verticesCount);

@@ -370,6 +370,7 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
     if (e == cudaSuccess) e = tree_emit_configure();
     if (e == cudaSuccess) e = collide_configure(&c->collide_grid);
     if (e == cudaSuccess) e = coop_sort_configure();
+    if (e == cudaSuccess) e = small_trees_configure();
     if (e != cudaSuccess)
     {
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -711,7 +712,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     if (tree->small)
     {
         // keys, sort, gather, leaves and all levels by one CTA
-        CU(launch_small_trees(true, tree->d_small, 1, s));
+        CU(launch_small_trees(true, tree->d_small, tree->T <= kSmallBitonicSplit ? 1u : 0u, 1, s));
         count_launch(ctx);
         tree->built = true;
         return OIBVH_OK;
@@ -779,17 +780,26 @@ static int batch_table_upload(oibvh_ctx* ctx, oibvh_ctx::BatchTable& tab, const 
     return OIBVH_OK;
 }
 
-static int small_batch_table(oibvh_ctx* ctx, const std::vector<oibvh_tree*>& list, const SmallTreeDesc** out)
+// table order: trees of up to kSmallBitonicSplit triangles first (their builds run the bitonic variant), then the rest
+static int small_batch_table(oibvh_ctx* ctx, const std::vector<oibvh_tree*>& list, const SmallTreeDesc** out,
+                             uint32_t* n_bitonic)
 {
     auto& tab = ctx->small_table;
     if (!(tab.dev && tab.key == list))
     {
-        std::vector<SmallTreeDesc> h(list.size());
-        for (size_t i = 0; i < list.size(); i++) h[i] = small_desc_of(list[i]);
+        std::vector<SmallTreeDesc> h;
+        h.reserve(list.size());
+        for (auto* t : list)
+            if (t->T <= kSmallBitonicSplit) h.push_back(small_desc_of(t));
+        const uint32_t first = (uint32_t)h.size();
+        for (auto* t : list)
+            if (t->T > kSmallBitonicSplit) h.push_back(small_desc_of(t));
         int rc = batch_table_upload(ctx, tab, list, h.data(), sizeof(SmallTreeDesc) * h.size());
         if (rc) return rc;
+        tab.total_blocks = first;
     }
     *out = static_cast<const SmallTreeDesc*>(tab.dev);
+    *n_bitonic = tab.total_blocks;
     return OIBVH_OK;
 }
 
@@ -816,13 +826,14 @@ extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
         // every small tree of the list in ONE launch, one CTA each
         DeviceGuard g(ctx->device);
         const SmallTreeDesc* table = nullptr;
-        int rc = small_batch_table(ctx, small_list, &table);
+        uint32_t n_bitonic = 0;
+        int rc = small_batch_table(ctx, small_list, &table, &n_bitonic);
         if (rc) return rc;
         for (auto* t : small_list)
             if ((rc = tree_flush_upload(t))) return rc;
         StageScope scope(ctx, OIBVH_STAGE_BUILD);
-        CU(launch_small_trees(true, table, (uint32_t)small_list.size(), ctx->stream));
-        count_launch(ctx);
+        CU(launch_small_trees(true, table, n_bitonic, (uint32_t)small_list.size(), ctx->stream));
+        count_launch(ctx, (n_bitonic ? 1 : 0) + (n_bitonic < small_list.size() ? 1 : 0));
         for (auto* t : small_list) t->built = true;
     }
     if (large_list.empty()) return OIBVH_OK;
@@ -911,7 +922,7 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
     }
     StageScope scope(ctx, OIBVH_STAGE_REFIT);
     if (tree->small)
-        CU(launch_small_trees(false, tree->d_small, 1, ctx->stream));
+        CU(launch_small_trees(false, tree->d_small, 0, 1, ctx->stream));
     else
         CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
                             ctx->stream));
@@ -935,12 +946,13 @@ extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
     if (small_list.size() >= 2)
     {
         const SmallTreeDesc* table = nullptr;
-        int rc = small_batch_table(ctx, small_list, &table);
+        uint32_t n_bitonic = 0;
+        int rc = small_batch_table(ctx, small_list, &table, &n_bitonic);
         if (rc) return rc;
         for (auto* t : small_list)
             if ((rc = tree_flush_upload(t))) return rc;
         StageScope scope(ctx, OIBVH_STAGE_REFIT);
-        CU(launch_small_trees(false, table, (uint32_t)small_list.size(), ctx->stream));
+        CU(launch_small_trees(false, table, n_bitonic, (uint32_t)small_list.size(), ctx->stream));
         count_launch(ctx);
     }
     for (uint32_t i = 0; i < n; i++)
@@ -966,17 +978,23 @@ static int transform_many_impl(oibvh_tree* const* trees, uint32_t n, const float
     auto& tab = ctx->xform_table;
     if (!(tab.dev && tab.key == list))
     {
-        std::vector<XformDesc> h(n);
         uint64_t blocks = 0;
+        for (uint32_t i = 0; i < n; i++) blocks += (trees[i]->V + 255) / 256;
+        REQUIRE(blocks < 0x7fffffffull, "too many vertices for one transform launch");
+        // n descriptors, then the tree index of every 256-vertex block
+        static_assert(sizeof(XformDesc) == 16, "descriptor layout");
+        std::vector<unsigned char> h(sizeof(XformDesc) * (size_t)n + sizeof(uint32_t) * (size_t)blocks);
+        XformDesc* hd = reinterpret_cast<XformDesc*>(h.data());
+        uint32_t* hb = reinterpret_cast<uint32_t*>(hd + n);
+        uint32_t next = 0;
         for (uint32_t i = 0; i < n; i++)
         {
-            h[i].pos = trees[i]->pos;
-            h[i].V = trees[i]->V;
-            h[i].block0 = (uint32_t)blocks;
-            blocks += (trees[i]->V + 255) / 256;
+            hd[i].pos = trees[i]->pos;
+            hd[i].V = trees[i]->V;
+            hd[i].block0 = next;
+            for (uint32_t b = 0; b < (trees[i]->V + 255) / 256; b++) hb[next++] = i;
         }
-        REQUIRE(blocks < 0x7fffffffull, "too many vertices for one transform launch");
-        int rc = batch_table_upload(ctx, tab, list, h.data(), sizeof(XformDesc) * n);
+        int rc = batch_table_upload(ctx, tab, list, h.data(), h.size());
         if (rc) return rc;
         tab.total_blocks = (uint32_t)blocks;
     }

@@ -64,13 +64,18 @@ struct SmallTreeDesc
     MeshAabb mesh;
     uint32_t T, L;
 };
-cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n, cudaStream_t s);
+// builds sort with a bitonic network up to kSmallBitonicSplit triangles and with a shared-memory radix sort above:
+// descs[0, n_bitonic) must be the trees of the first kind, descs[n_bitonic, n) the others (refits do not care)
+constexpr uint32_t kSmallBitonicSplit = 512;
+cudaError_t small_trees_configure();
+cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n_bitonic, uint32_t n, cudaStream_t s);
 struct XformDesc
 {
     float4* pos;
     uint32_t V;
     uint32_t block0; // first 256-vertex block of this tree in the launch
 };
+// descs: n descriptors followed by total_blocks uint32 (the tree of every 256-vertex block)
 cudaError_t launch_transform_many(const XformDesc* descs, uint32_t n, uint32_t total_blocks, const float* mats,
                                   cudaStream_t s);
 

@@ -788,19 +788,135 @@ __global__ void __launch_bounds__(256) transform_kernel(float4* __restrict__ pos
 // dropped right child copies its left child.
 // =================================================================================================
 constexpr int kSmallThreads = 128;
+constexpr int kSmallSmemLevel = 512; // levels of at most this many nodes are kept in shared memory (6 x 2 KB)
+constexpr int kSmallBitonicMax = 2048; // static-shared-memory variant (bitonic network); must hold 6 x kSmallSmemLevel floats
 
-template <bool BUILD>
+__device__ __forceinline__ Box smem_box(const float* s_box, uint32_t i)
+{
+    Box b;
+    b.lx = s_box[i];
+    b.ly = s_box[kSmallSmemLevel + i];
+    b.lz = s_box[2 * kSmallSmemLevel + i];
+    b.hx = s_box[3 * kSmallSmemLevel + i];
+    b.hy = s_box[4 * kSmallSmemLevel + i];
+    b.hz = s_box[5 * kSmallSmemLevel + i];
+    return b;
+}
+
+// Stable sort for 512 < T <= 4096 inside one CTA: LSD radix, four 8-bit digits. The keys stay where they were
+// computed (key[input index]); what moves is the 16-bit input index, ping-pong between two shared arrays (48 KB in
+// all, four CTAs per SM). Each warp owns a contiguous quarter of the sequence and ranks it 32 entries per step with
+// shared-memory peer masks (the ranking of onesweep_pass_kernel); ranks are parked in shared memory, a 256-entry scan
+// turns the per-warp digit counts into bases, and the indices move to the other array. About 110 instructions per key
+// for the whole sort, against ~550 for a bitonic network at T = 4096.
+struct SmallRadixSmem
+{
+    uint32_t key[kSmallTreeMax];    // by input index
+    uint16_t id[kSmallTreeMax];     // current order (result)
+    uint16_t rank[kSmallTreeMax];   // \ after the sort these two arrays (16 KB, contiguous)
+    uint16_t id_alt[kSmallTreeMax]; // / are reused for the shared tree levels
+    uint2 tab[kSmallThreads / 32][256]; // (.x running count -> slot base, .y peer mask)
+    uint32_t scan[kSmallThreads / 32];
+};
+static_assert(2 * sizeof(uint16_t) * kSmallTreeMax >= sizeof(float) * 6 * kSmallSmemLevel, "room for the shared levels");
+
+__device__ __forceinline__ void small_radix_sort(SmallRadixSmem& sm, uint32_t T)
+{
+    constexpr int WARPS = kSmallThreads / 32;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t chunk = (((T + WARPS - 1) / WARPS) + 31) & ~31u; // entries per warp, whole steps of 32
+    const uint32_t lane_bit = 1u << lane;
+    uint2* my_tab = sm.tab[warp];
+    for (uint32_t i = tid; i < T; i += kSmallThreads) sm.id[i] = (uint16_t)i;
+    for (int pass = 0; pass < 4; pass++)
+    {
+        const uint16_t* src = (pass & 1) ? sm.id_alt : sm.id;
+        uint16_t* dst = (pass & 1) ? sm.id : sm.id_alt;
+        const uint32_t shift = 8 * pass;
+        for (uint32_t i = tid; i < WARPS * 256; i += kSmallThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
+        __syncthreads();
+        for (uint32_t s = 0; s < chunk; s += 32)
+        {
+            const uint32_t i = warp * chunk + s + lane;
+            const bool valid = i < T;
+            const uint32_t dgt = valid ? (sm.key[src[i]] >> shift) & 255u : 0u;
+            if (valid) atomicOr(&my_tab[dgt].y, lane_bit);
+            __syncwarp();
+            uint2 e = make_uint2(0u, 0u);
+            if (valid) e = my_tab[dgt]; // (count before this step, peers of this step)
+            const uint32_t lower = __popc(e.y & lanemask_lt());
+            if (valid) sm.rank[i] = (uint16_t)(e.x + lower);
+            __syncwarp();
+            if (valid && lower == 0) my_tab[dgt] = make_uint2(e.x + __popc(e.y), 0u); // lowest lane closes the group
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit bases: exclusive over (digit, warp); two digits per thread
+        {
+            static_assert(kSmallThreads * 2 == 256, "two digits per thread");
+            uint32_t tot[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                const uint32_t dg = 2 * tid + q;
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; w++)
+                {
+                    const uint32_t c = sm.tab[w][dg].x;
+                    sm.tab[w][dg].x = run;
+                    run += c;
+                }
+                tot[q] = run;
+            }
+            const uint32_t pair = tot[0] + tot[1];
+            const uint32_t base = block_exclusive_scan<kSmallThreads>(pair, sm.scan);
+#pragma unroll
+            for (int w = 0; w < WARPS; w++)
+            {
+                sm.tab[w][2 * tid].x += base;
+                sm.tab[w][2 * tid + 1].x += base + tot[0];
+            }
+        }
+        __syncthreads();
+        for (uint32_t s = 0; s < chunk; s += 32)
+        {
+            const uint32_t i = warp * chunk + s + lane;
+            if (i < T)
+            {
+                const uint16_t id = src[i];
+                dst[my_tab[(sm.key[id] >> shift) & 255u].x + sm.rank[i]] = id;
+            }
+        }
+        __syncthreads();
+    }
+    // four passes: the result is back in sm.id
+}
+
+// RADIX selects the sort of a build: false = bitonic network in static shared memory (T <= kSmallBitonicMax; the
+// host sends trees of up to kSmallBitonicSplit triangles here), true = small_radix_sort in 80 KB of dynamic shared
+// memory (T <= kSmallTreeMax). Refits ignore it.
+template <bool BUILD, bool RADIX>
 __global__ void __launch_bounds__(kSmallThreads) small_tree_kernel(const SmallTreeDesc* __restrict__ descs)
 {
-    __shared__ unsigned long long s_kv[BUILD ? kSmallTreeMax : 1];
+    extern __shared__ __align__(16) unsigned char small_dyn[];
+    __shared__ unsigned long long s_kv_static[(BUILD && !RADIX) ? kSmallBitonicMax : 1];
+    __shared__ float s_box_refit[BUILD ? 1 : 6 * kSmallSmemLevel];
+    SmallRadixSmem& rs = *reinterpret_cast<SmallRadixSmem*>(small_dyn);
+    unsigned long long* s_kv = s_kv_static;
+    // a build is done with the sort buffers by the time the levels start: the shared levels reuse them
+    float* s_box = !BUILD ? s_box_refit : (RADIX ? reinterpret_cast<float*>(rs.rank) : reinterpret_cast<float*>(s_kv_static));
+    static_assert(sizeof(unsigned long long) * kSmallBitonicMax >= sizeof(float) * 6 * kSmallSmemLevel,
+                  "the bitonic buffer is reused for the shared levels");
     const SmallTreeDesc d = descs[blockIdx.x];
     const uint32_t T = d.T, L = d.L, tid = threadIdx.x;
     float2* nodes = reinterpret_cast<float2*>(d.nodes);
     const uint32_t leaf_off = level_offset(T, L, L);
     if (BUILD)
     {
-        const uint32_t P = 1u << L; // padded to a power of two; padding sorts last
-        for (uint32_t i = tid; i < P; i += kSmallThreads)
+        const uint32_t P = RADIX ? T : 1u << L; // bitonic: padded to a power of two; padding sorts last
+#pragma unroll 4
+        for (uint32_t i = tid; i < P; i += kSmallThreads) // independent iterations: several gathers in flight
         {
             unsigned long long kv = ~0ull;
             if (i < T)
@@ -808,32 +924,49 @@ __global__ void __launch_bounds__(kSmallThreads) small_tree_kernel(const SmallTr
                 const uint4 f = d.faces_in[i];
                 const uint32_t key = morton_of_box(box_of(d.pos[f.x], d.pos[f.y], d.pos[f.z]), d.mesh);
                 kv = ((unsigned long long)key << 32) | i;
+                if (RADIX) rs.key[i] = key;
             }
-            s_kv[i] = kv;
+            if (!RADIX) s_kv[i] = kv;
         }
         __syncthreads();
-        // bitonic network on the 64-bit composites (all distinct, so the result is the stable order)
-        for (uint32_t k = 2; k <= P; k <<= 1)
-            for (uint32_t j = k >> 1; j > 0; j >>= 1)
-            {
-                for (uint32_t t = tid; t < (P >> 1); t += kSmallThreads)
+        if (RADIX)
+            small_radix_sort(rs, T);
+        else
+        {
+            // bitonic network on the 64-bit composites (all distinct, so the result is the stable order)
+            for (uint32_t k = 2; k <= P; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1)
                 {
-                    const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const uint32_t hi = lo | j;
-                    const unsigned long long a = s_kv[lo], b = s_kv[hi];
-                    if ((a > b) == ((lo & k) == 0))
+                    for (uint32_t t = tid; t < (P >> 1); t += kSmallThreads)
                     {
-                        s_kv[lo] = b;
-                        s_kv[hi] = a;
+                        const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const uint32_t hi = lo | j;
+                        const unsigned long long a = s_kv[lo], b = s_kv[hi];
+                        if ((a > b) == ((lo & k) == 0))
+                        {
+                            s_kv[lo] = b;
+                            s_kv[hi] = a;
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
-            }
+        }
+#pragma unroll 4
         for (uint32_t i = tid; i < T; i += kSmallThreads)
         {
-            const unsigned long long kv = s_kv[i];
-            const uint32_t id = (uint32_t)kv;
-            d.keys[i] = (uint32_t)(kv >> 32);
+            uint32_t id, key;
+            if (RADIX)
+            {
+                id = rs.id[i];
+                key = rs.key[id];
+            }
+            else
+            {
+                const unsigned long long kv = s_kv[i];
+                id = (uint32_t)kv;
+                key = (uint32_t)(kv >> 32);
+            }
+            d.keys[i] = key;
             d.perm[i] = id;
             const uint4 f = d.faces_in[id];
             d.faces[3 * i] = f.x;
@@ -844,42 +977,85 @@ __global__ void __launch_bounds__(kSmallThreads) small_tree_kernel(const SmallTr
     }
     else
     {
-        for (uint32_t i = tid; i < T; i += kSmallThreads)
+#pragma unroll 4
+        for (uint32_t i = tid; i < T; i += kSmallThreads) // independent iterations: several gathers in flight
         {
             const uint32_t a = d.faces[3 * i], b = d.faces[3 * i + 1], c = d.faces[3 * i + 2];
             store_box(nodes, leaf_off + i, box_of(d.pos[a], d.pos[b], d.pos[c]));
         }
     }
-    // inner levels, bottom-up; the children were written by this CTA (read back through L2)
+    // inner levels, bottom-up. Wide levels read their children back through L2 (written by this CTA); from the
+    // first level of at most kSmallSmemLevel nodes on, the level just produced also stays in shared memory, so the
+    // ~10 top levels cost two CTA barriers each instead of an L2 round trip.
     uint32_t child_off = leaf_off, child_cnt = T;
+    bool child_in_smem = false;
     for (int l = (int)L - 1; l >= 0; l--)
     {
-        __syncthreads();
         const uint32_t cnt = level_count(T, L, (uint32_t)l), off = level_offset(T, L, (uint32_t)l);
-        for (uint32_t p = tid; p < cnt; p += kSmallThreads)
+        __syncthreads(); // the children are complete
+        if (cnt > (uint32_t)kSmallSmemLevel)
         {
-            Box b = load_box_cg(nodes, child_off + 2 * p);
-            if (2 * p + 1 < child_cnt) b = box_merge(b, load_box_cg(nodes, child_off + 2 * p + 1));
-            store_box(nodes, off + p, b);
+#pragma unroll 2
+            for (uint32_t p = tid; p < cnt; p += kSmallThreads)
+            {
+                Box b = load_box_cg(nodes, child_off + 2 * p);
+                if (2 * p + 1 < child_cnt) b = box_merge(b, load_box_cg(nodes, child_off + 2 * p + 1));
+                store_box(nodes, off + p, b);
+            }
+        }
+        else
+        {
+            constexpr int PER = kSmallSmemLevel / kSmallThreads;
+            Box mine[PER];
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+            {
+                const uint32_t p = tid + k * kSmallThreads;
+                if (p < cnt)
+                {
+                    if (child_in_smem)
+                    {
+                        mine[k] = smem_box(s_box, 2 * p);
+                        if (2 * p + 1 < child_cnt) mine[k] = box_merge(mine[k], smem_box(s_box, 2 * p + 1));
+                    }
+                    else
+                    {
+                        mine[k] = load_box_cg(nodes, child_off + 2 * p);
+                        if (2 * p + 1 < child_cnt)
+                            mine[k] = box_merge(mine[k], load_box_cg(nodes, child_off + 2 * p + 1));
+                    }
+                }
+            }
+            __syncthreads(); // every child has been read: the parents may overwrite the shared level
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+            {
+                const uint32_t p = tid + k * kSmallThreads;
+                if (p < cnt)
+                {
+                    store_box(nodes, off + p, mine[k]);
+                    float* o = s_box + p;
+                    o[0] = mine[k].lx;
+                    o[kSmallSmemLevel] = mine[k].ly;
+                    o[2 * kSmallSmemLevel] = mine[k].lz;
+                    o[3 * kSmallSmemLevel] = mine[k].hx;
+                    o[4 * kSmallSmemLevel] = mine[k].hy;
+                    o[5 * kSmallSmemLevel] = mine[k].hz;
+                }
+            }
+            child_in_smem = true;
         }
         child_off = off;
         child_cnt = cnt;
     }
 }
 
-// Rigid transforms of many trees in one launch: block -> (tree, 256-vertex chunk) through the block prefix table.
+// Rigid transforms of many trees in one launch: block -> tree through the block map that follows the n descriptors.
 __global__ void __launch_bounds__(256) transform_many_kernel(const XformDesc* __restrict__ descs, uint32_t n,
                                                              const float* __restrict__ mats)
 {
-    uint32_t lo = 0, hi = n; // largest i with descs[i].block0 <= blockIdx.x
-    while (hi - lo > 1)
-    {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (descs[mid].block0 <= blockIdx.x)
-            lo = mid;
-        else
-            hi = mid;
-    }
+    const uint32_t* block_tree = reinterpret_cast<const uint32_t*>(descs + n);
+    const uint32_t lo = block_tree[blockIdx.x];
     const XformDesc d = descs[lo];
     const uint32_t i = (blockIdx.x - d.block0) * 256 + threadIdx.x;
     if (i >= d.V) return;
@@ -997,13 +1173,24 @@ cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n, cudaStream_t s)
+cudaError_t small_trees_configure()
+{
+    return cudaFuncSetAttribute(small_tree_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(SmallRadixSmem));
+}
+
+// descs[0, n_bitonic) have T <= kSmallBitonicSplit (bitonic build), descs[n_bitonic, n) the rest (radix build)
+cudaError_t launch_small_trees(bool build, const SmallTreeDesc* descs, uint32_t n_bitonic, uint32_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    if (build)
-        small_tree_kernel<true><<<n, kSmallThreads, 0, s>>>(descs);
-    else
-        small_tree_kernel<false><<<n, kSmallThreads, 0, s>>>(descs);
+    if (!build)
+    {
+        small_tree_kernel<false, false><<<n, kSmallThreads, 0, s>>>(descs);
+        return cudaGetLastError();
+    }
+    if (n_bitonic) small_tree_kernel<true, false><<<n_bitonic, kSmallThreads, 0, s>>>(descs);
+    if (n > n_bitonic)
+        small_tree_kernel<true, true><<<n - n_bitonic, kSmallThreads, sizeof(SmallRadixSmem), s>>>(descs + n_bitonic);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "oibvh/oibvh.hpp"
 
@@ -73,6 +74,55 @@ int main(int argc, char** argv)
             tree2->refit();
             scene.detectCollision(DeviceType::GPU0, 4, 3);
             printf("frame %d pairs %u\n", frame, scene.getIntTriPairCount());
+        }
+        // many-body extension: 27 small spheres on a grid, built / moved / refitted with one launch per step,
+        // against the same scene handled one object at a time like the reference's loops
+        {
+            std::vector<std::shared_ptr<Mesh>> meshesA, meshesB;
+            std::vector<std::shared_ptr<OibvhTree>> many, single;
+            std::vector<oibvh_math::mat4> mats;
+            for (int i = 0; i < 27; i++)
+            {
+                const oibvh_math::vec3 c(1.6f * (float)(i % 3), 1.6f * (float)((i / 3) % 3), 1.6f * (float)(i / 9));
+                for (int copy = 0; copy < 2; copy++)
+                {
+                    auto m = uvSphere(8 + (unsigned)(i % 4));
+                    m->translate(c);
+                    (copy ? meshesB : meshesA).push_back(m);
+                    // trees are created on the translated meshes (m_aabb is fixed at Mesh construction, as in the reference)
+                    (copy ? single : many).push_back(std::make_shared<OibvhTree>(m));
+                }
+                mats.push_back(oibvh_math::translate(oibvh_math::identity(),
+                                                     oibvh_math::vec3(0.05f * (float)(i % 5), -0.03f * (float)(i % 3), 0.0f)));
+            }
+            OibvhTree::buildMany(many);
+            for (auto& t : single) t->build();
+            Scene sm, ss;
+            for (auto& t : many) sm.addOibvhTree(t);
+            for (auto& t : single) ss.addOibvhTree(t);
+            sm.detectCollision(DeviceType::GPU0, 4, 3);
+            ss.detectCollision(DeviceType::GPU0, 4, 3);
+            const unsigned p0m = sm.getIntTriPairCount(), p0s = ss.getIntTriPairCount();
+            OibvhTree::transformMany(many, mats);
+            OibvhTree::refitManyOnDevice(many);
+            for (size_t i = 0; i < single.size(); i++)
+            {
+                meshesB[i]->transform(mats[i]);
+                single[i]->refit();
+            }
+            sm.detectCollision(DeviceType::GPU0, 4, 3);
+            ss.detectCollision(DeviceType::GPU0, 4, 3);
+            bool same_nodes = true;
+            for (size_t i = 0; i < many.size(); i++)
+            {
+                many[i]->syncHost();
+                single[i]->syncHost();
+                same_nodes = same_nodes && many[i]->m_aabbTree.size() == single[i]->m_aabbTree.size() &&
+                             memcmp(many[i]->m_aabbTree.data(), single[i]->m_aabbTree.data(),
+                                    sizeof(aabb_box_t) * many[i]->m_aabbTree.size()) == 0;
+            }
+            printf("manybody bodies %zu pairs %u %u moved %u %u same_nodes %d\n", many.size(), p0m, p0s,
+                   sm.getIntTriPairCount(), ss.getIntTriPairCount(), same_nodes ? 1 : 0);
         }
         // root box sanity: tree root == union of leaf boxes == mesh bounds
         const aabb_box_t& root = tree1->m_aabbTree[0];

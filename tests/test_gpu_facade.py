@@ -22,6 +22,11 @@ def test_facade_demo_matches_golden(tmp_path, golden, ctx):
     assert np.array_equal(pairs, golden["collide"]["sphere64_pairs"])
     frames = [l for l in res.stdout.splitlines() if l.startswith("frame")]
     assert len(frames) == 3
+    # many-body helpers (buildMany / transformMany / refitManyOnDevice) == the per-object loops
+    mb = [l.split() for l in res.stdout.splitlines() if l.startswith("manybody")]
+    assert len(mb) == 1, res.stdout
+    mb = mb[0]
+    assert mb[2] == "27" and mb[4] == mb[5] and int(mb[4]) > 0 and mb[7] == mb[8] and int(mb[7]) > 0 and mb[10] == "1", mb
 
 
 def test_facade_header_mirrors_reference_surface():
