@@ -185,7 +185,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // the fence is cumulative over the CTA barrier, so every thread's earlier global writes are visible to every
 // thread of the grid afterwards (readers must bypass L1: __ldcg / ld.relaxed.gpu). A bounded spin turns a would-be
 // hang into a failure flag.
-__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation, uint32_t* fail_flag)
+// `participants` = number of CTAs that arrive at this counter (the whole grid, or one job's CTA range).
+__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation, uint32_t* fail_flag,
+                                          uint32_t participants)
 {
     __syncthreads();
     if (threadIdx.x == 0)
@@ -193,7 +195,7 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation
         // release-arrive / acquire-poll: the release is cumulative over the CTA barrier above, the acquire orders
         // everything after the barrier below -- no separate membar round trips
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        const uint32_t target = generation * gridDim.x;
+        const uint32_t target = generation * participants;
         uint32_t spins = 0;
         while (ld_acquire_gpu(counter) < target)
         {

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) coop_sort_kernel(const SortSe
             }
         }
         COOP_STAMP(3);
-        grid_sync(sync_ctl, ++gen, sync_ctl + 1);
+        grid_sync(ctl, ++gen, ctl + 1, G);
         COOP_STAMP(4);
 
         // ---- one warp scans each digit row (exclusive prefix over CTAs) and records the row total ----
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) coop_sort_kernel(const SortSe
             }
         }
         COOP_STAMP(5);
-        grid_sync(sync_ctl, ++gen, sync_ctl + 1);
+        grid_sync(ctl, ++gen, ctl + 1, G);
         COOP_STAMP(6);
 
         // ---- global base of every digit for this CTA: (scan of the row totals) + (row prefix at this CTA) ----
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) coop_sort_kernel(const SortSe
             }
         }
         COOP_STAMP(8);
-        if (pass + 1 < kRadixPasses) grid_sync(sync_ctl, ++gen, sync_ctl + 1);
+        if (pass + 1 < kRadixPasses) grid_sync(ctl, ++gen, ctl + 1, G);
         COOP_STAMP(9);
         // ping-pong
         uint32_t* nk = kout;

@@ -14,8 +14,9 @@ ap.add_argument("--nv", type=int, default=bench.NV)
 ap.add_argument("--entry", type=int, default=bench.ENTRY_LEVEL)
 ap.add_argument("--expand", type=int, default=bench.EXPAND_LEVELS)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--grid-order", action="store_true", help="keep the generator's face order instead of shuffling it")
 a = ap.parse_args()
-pos, faces = bench.make_meshes(a.nu, a.nv)
+pos, faces = bench.make_meshes(a.nu, a.nv, shuffle=not a.grid_order)
 mA = ob.Mesh(pos, faces); mB = mA.copy()
 ctx = ob.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=0)
