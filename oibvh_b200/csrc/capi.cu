@@ -60,6 +60,10 @@ struct oibvh_ctx
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr; // host->device uploads run here and overlap compute on `stream`
+    // independent launches of one call (the emit kernels of a multi-tree build) alternate between `stream` and this
+    // one, forked / joined with events, so the partially filled last wave of one kernel is topped up by the next
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t launches = 0;
     bool timing = false;
     bool capturing = false;
@@ -367,6 +371,9 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
         c->own_stream = true;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = tree_emit_configure();
     if (e == cudaSuccess) e = collide_configure(&c->collide_grid);
     if (e == cudaSuccess) e = coop_sort_configure();
@@ -403,6 +410,13 @@ extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
+    if (ctx->aux_stream)
+    {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->small_table.dev);
     cudaFree(ctx->xform_table.dev);
@@ -900,13 +914,20 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
         CU(e);
         count_launch(ctx);
     }
+    // the emit kernels are independent: odd trees go to the auxiliary stream, so the kernels share the machine and
+    // the wave quantisation of each (1024 CTAs on 444 slots = 2.3 -> 3 waves) is paid once for all of them
+    CU(cudaEventRecord(ctx->ev_fork, s));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (uint32_t i = 0; i < n; i++)
     {
         oibvh_tree* t = trees[i];
-        CU(launch_tree_emit(true, t->faces_in, t->vals_a, t->faces, t->pos, t->nodes, t->T, t->done_counter, s));
+        CU(launch_tree_emit(true, t->faces_in, t->vals_a, t->faces, t->pos, t->nodes, t->T, t->done_counter,
+                            (i & 1) ? ctx->aux_stream : s));
         count_launch(ctx);
         t->built = true;
     }
+    CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     return OIBVH_OK;
 }
 
@@ -955,12 +976,39 @@ extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
         CU(launch_small_trees(false, table, n_bitonic, (uint32_t)small_list.size(), ctx->stream));
         count_launch(ctx);
     }
+    // the remaining trees one launch each; independent launches alternate between the two streams (see build_many)
+    std::vector<oibvh_tree*> rest;
     for (uint32_t i = 0; i < n; i++)
-        if (!trees[i]->small || small_list.size() < 2)
+        if (!trees[i]->small || small_list.size() < 2) rest.push_back(trees[i]);
+    if (rest.size() < 2)
+    {
+        for (auto* t : rest)
         {
-            int rc = oibvh_tree_refit(trees[i]);
+            int rc = oibvh_tree_refit(t);
             if (rc) return rc;
         }
+        return OIBVH_OK;
+    }
+    for (auto* t : rest)
+    {
+        int rc = tree_flush_upload(t);
+        if (rc) return rc;
+    }
+    StageScope scope(ctx, OIBVH_STAGE_REFIT);
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    for (size_t i = 0; i < rest.size(); i++)
+    {
+        oibvh_tree* t = rest[i];
+        cudaStream_t st = (i & 1) ? ctx->aux_stream : ctx->stream;
+        if (t->small)
+            CU(launch_small_trees(false, t->d_small, 0, 1, st));
+        else
+            CU(launch_tree_emit(false, nullptr, nullptr, t->faces, t->pos, t->nodes, t->T, t->done_counter, st));
+        count_launch(ctx);
+    }
+    CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     return OIBVH_OK;
 }
 
