@@ -17,6 +17,7 @@
 //     reference tree); otherwise the minimal oibvh::vec types below, which follow glm's arithmetic order exactly.
 // Header-only; link with -loibvh_b200.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -336,6 +337,21 @@ public:
                                                       reinterpret_cast<const float*>(mats.data())));
     }
 
+    // OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:69-124) without the GL upload: wireframe boxes of the
+    // first min(internal nodes, 256) nodes into m_vertices (8 corners per box) / m_indices (12 edges per box)
+    void convertToVertexArray()
+    {
+        uint32_t T = 0, N = 0, n = 0;
+        oibvh_detail::check(oibvh_tree_get_info(m_handle, &T, nullptr, &N, nullptr));
+        const uint32_t boxes = std::min<uint32_t>(N - T, 256u);
+        m_vertices.resize((size_t)boxes * 8);
+        m_indices.resize((size_t)boxes * 24);
+        oibvh_detail::check(oibvh_tree_box_wireframe(m_handle, 256u, reinterpret_cast<float*>(m_vertices.data()),
+                                                     m_indices.data(), &n));
+    }
+    std::vector<oibvh_math::vec3> m_vertices;    // (after convertToVertexArray)
+    std::vector<unsigned int> m_indices;
+
     std::vector<aabb_box_t> m_aabbTree;          // N nodes, real-index order (after syncHost)
     std::vector<oibvh_math::uvec3> m_faces;      // Morton-sorted faces (after syncHost)
     std::vector<oibvh_math::vec3> m_positions;   // (after syncHost)
@@ -412,6 +428,15 @@ public:
     }
     unsigned int getIntTriPairCount() const { return m_intTriPairCount; }
     unsigned int getCandidateCount() const { return m_candidateCount; } // extension
+    // Scene::convertToVertexArray (src/cuda/scene.cu:68-93) without the GL upload: m_vertices = six vec3 per pair
+    // (triangle A, then triangle B), gathered on the device from the trees' current positions
+    void convertToVertexArray()
+    {
+        m_vertices.resize((size_t)m_intTriPairCount * 6);
+        static_assert(sizeof(oibvh_math::vec3) == 12, "vec3 is three packed floats");
+        oibvh_detail::check(oibvh_scene_pair_vertices(m_handle, reinterpret_cast<float*>(m_vertices.data())));
+    }
+    std::vector<oibvh_math::vec3> m_vertices;
 
     std::vector<int_tri_pair_node_t> m_intTriPairs; // {bvhA < bvhB, triA, triB}; tri = Morton-sorted position
 

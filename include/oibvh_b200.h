@@ -187,6 +187,21 @@ int oibvh_scene_pair_capacity(oibvh_scene* scene, uint32_t* capacity);
  * Returns the number of rounds written (<= max_rounds). */
 int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds, uint32_t* n_rounds);
 
+/* Scene::convertToVertexArray (src/cuda/scene.cu:68-93) as a device-side gather: pair i of the last detection
+ * contributes six packed float3 (A.v0, A.v1, A.v2, B.v0, B.v1, B.v2) = 18 floats, in the order of the pair list.
+ * _device: enqueue only, into a caller-provided DEVICE buffer of capacity_pairs * 18 floats; the pair count is read
+ * on the device (min(n_pairs, capacity_pairs) records are written), so the call can follow oibvh_scene_detect_async
+ * on the stream or sit inside a captured frame graph -- a renderer consumes the result without any D2H of pair lists.
+ * The host variant synchronises and writes n_pairs * 18 floats. */
+int oibvh_scene_pair_vertices_device(oibvh_scene* scene, float* dev_vertices, uint32_t capacity_pairs);
+int oibvh_scene_pair_vertices(oibvh_scene* scene, float* host_vertices);
+/* OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:69-124, makeCube src/utils/utils.cpp:15-70): wireframe
+ * boxes of the first min(internal nodes, max_nodes) nodes (the reference draws 256): 8 corners (24 floats) and 12
+ * edges (24 indices, offset by 8 per box) each, corner arithmetic as in the reference. Host buffers; *n_boxes
+ * receives the number of boxes written. Synchronises. */
+int oibvh_tree_box_wireframe(oibvh_tree* tree, uint32_t max_nodes, float* host_vertices, uint32_t* host_indices,
+                             uint32_t* n_boxes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,9 @@ _SIGNATURES = {
     "oibvh_scene_device_counters": (C.c_int, [_vp, C.POINTER(_vp)]),
     "oibvh_scene_pair_capacity": (C.c_int, [_vp, _u32p]),
     "oibvh_scene_get_round_stats": (C.c_int, [_vp, _u32p, _u32, _u32p]),
+    "oibvh_scene_pair_vertices_device": (C.c_int, [_vp, _vp, _u32]),
+    "oibvh_scene_pair_vertices": (C.c_int, [_vp, _vp]),
+    "oibvh_tree_box_wireframe": (C.c_int, [_vp, _u32, _vp, _vp, _u32p]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _fn = getattr(_lib, _name)  # AttributeError here = the library does not export what the header declares
@@ -435,6 +438,19 @@ class OibvhTree:
         m = np.ascontiguousarray(M, np.float32).reshape(16)
         _check(_lib.oibvh_tree_transform(self._h, m.ctypes.data_as(_f32p)))
 
+    def convertToVertexArray(self, max_nodes=256):
+        """OibvhTree::convertToVertexArray (oibvhTree.cu:69-124): wireframe boxes of the first min(internal, 256)
+        nodes -> (vertices [n*8, 3] float32, indices [n*24] uint32)"""
+        T, V, N, _ = self.info()
+        n = min(N - T, int(max_nodes))
+        verts = np.empty((n * 8, 3), np.float32)
+        idx = np.empty(n * 24, np.uint32)
+        got = _u32()
+        _check(_lib.oibvh_tree_box_wireframe(self._h, int(max_nodes), _ptr(verts) if n else None,
+                                             _ptr(idx) if n else None, C.byref(got)))
+        assert got.value == n
+        return verts, idx
+
     def download(self, nodes=True, faces=True, perm=True):
         T, V, N, _ = self.info()
         out = {}
@@ -586,6 +602,26 @@ class Scene:
         out = np.empty((n.value, 4), np.uint32)
         _check(_lib.oibvh_scene_get_pairs(self._h, _ptr(out) if n.value else None))
         return out
+
+    def convertToVertexArray(self):
+        """Scene::convertToVertexArray (scene.cu:68-93): [n_pairs * 6, 3] float32 -- per pair the three vertices of
+        the A triangle, then of the B triangle, gathered on the device"""
+        n, _ = self.counts()
+        out = np.empty((n * 6, 3), np.float32)
+        _check(_lib.oibvh_scene_pair_vertices(self._h, _ptr(out) if n else None))
+        self.m_vertices = out
+        return out
+
+    def pair_vertices_device(self, dev_ptr, capacity_pairs):
+        """enqueue the same gather into a caller-provided device buffer (no sync, graph-capturable)"""
+        _check(_lib.oibvh_scene_pair_vertices_device(self._h, _vp(int(dev_ptr)), int(capacity_pairs)))
+
+    def get_pairs_into(self, host_ptr):
+        """oibvh_scene_get_pairs into a caller-owned host buffer (e.g. pinned); returns the pair count"""
+        n, _ = self.counts()
+        if n:
+            _check(_lib.oibvh_scene_get_pairs(self._h, _vp(int(host_ptr))))
+        return n
 
     # -- extensions --
     def set_shard(self, rank, world):

@@ -1404,6 +1404,75 @@ extern "C" int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_
     return OIBVH_OK;
 }
 
+extern "C" int oibvh_scene_pair_vertices_device(oibvh_scene* scene, float* dev_vertices, uint32_t capacity_pairs)
+{
+    REQUIRE(scene && dev_vertices, "NULL argument");
+    REQUIRE(scene->pairs != nullptr && !scene->objs_dirty, "run a detection first");
+    oibvh_ctx* ctx = scene->ctx;
+    DeviceGuard g(ctx->device);
+    CU(launch_pair_vertices(scene->d_objs, scene->pairs, scene->pair_cap, scene->counters, dev_vertices,
+                            capacity_pairs, ctx->stream));
+    count_launch(ctx);
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_pair_vertices(oibvh_scene* scene, float* host_vertices)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    uint32_t n = 0;
+    int rc = oibvh_scene_get_counts(scene, &n, nullptr); // also regrows the queues / re-runs after an overflow
+    if (rc) return rc;
+    if (n == 0) return OIBVH_OK;
+    REQUIRE(host_vertices != nullptr, "host_vertices is NULL");
+    oibvh_ctx* ctx = scene->ctx;
+    DeviceGuard g(ctx->device);
+    float* d = nullptr;
+    rc = dev_alloc(&d, (size_t)n * 18);
+    if (rc) return rc;
+    cudaError_t e = launch_pair_vertices(scene->d_objs, scene->pairs, scene->pair_cap, scene->counters, d, n, ctx->stream);
+    count_launch(ctx);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_vertices, d, sizeof(float) * 18 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "pair_vertices: %s", cudaGetErrorString(e));
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_box_wireframe(oibvh_tree* tree, uint32_t max_nodes, float* host_vertices,
+                                        uint32_t* host_indices, uint32_t* n_boxes)
+{
+    REQUIRE(tree && n_boxes, "NULL argument");
+    REQUIRE(tree->built, "tree is not built (OibvhTree::convertToVertexArray asserts m_buildDone)");
+    const uint32_t n = std::min(tree->N - tree->T, max_nodes);
+    *n_boxes = n;
+    if (n == 0) return OIBVH_OK;
+    REQUIRE(host_vertices && host_indices, "NULL output buffer");
+    oibvh_ctx* ctx = tree->ctx;
+    DeviceGuard g(ctx->device);
+    float* dv = nullptr;
+    uint32_t* di = nullptr;
+    int rc = dev_alloc(&dv, (size_t)n * 24);
+    if (rc) return rc;
+    rc = dev_alloc(&di, (size_t)n * 24);
+    if (rc)
+    {
+        cudaFree(dv);
+        return rc;
+    }
+    cudaError_t e = launch_box_wireframe(tree->nodes, n, dv, di, ctx->stream);
+    count_launch(ctx);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_vertices, dv, sizeof(float) * 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_indices, di, sizeof(uint32_t) * 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dv);
+    cudaFree(di);
+    if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "box_wireframe: %s", cudaGetErrorString(e));
+    return OIBVH_OK;
+}
+
 extern "C" int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases,
                                             uint32_t* n_phases)
 {

@@ -573,6 +573,92 @@ __global__ void __launch_bounds__(kColThreads, 1)
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = n_stamps; // number of stamps
 }
 
+// =================================================================================================
+// Collided-triangle vertex stream: Scene::convertToVertexArray (src/cuda/scene.cu:68-93) as a device-side gather.
+// Pair i contributes six packed float3: the three vertices of the A triangle, then of the B triangle. The pair
+// count is read from the counters block, so the launch can follow a detection on the stream (or sit in its graph)
+// without a host round trip.
+// =================================================================================================
+__global__ void __launch_bounds__(256) pair_vertices_kernel(const ObjDesc* __restrict__ objs,
+                                                            const uint4* __restrict__ pairs, uint32_t pair_cap,
+                                                            const uint32_t* __restrict__ counters,
+                                                            float* __restrict__ out, uint32_t out_cap_pairs)
+{
+    const uint32_t n = min(min(__ldcg(counters + CTR_PAIRS), pair_cap), out_cap_pairs);
+    const uint32_t total = n * 6u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t p = i / 6u, j = i - p * 6u;       // j = 0..2: triangle A, 3..5: triangle B
+        const uint4 rec = __ldcg(pairs + p);             // (objA, objB, triA, triB), written by the collide kernel
+        const uint32_t side = j >= 3u ? 1u : 0u;
+        const ObjDesc o = objs[side ? rec.y : rec.x];
+        const uint32_t tri = side ? rec.w : rec.z;
+        const uint32_t vi = __ldg(o.faces + 3ull * tri + (j - 3u * side));
+        const float4 v = __ldg(o.pos + vi);
+        float* dst = out + 3ull * i;
+        dst[0] = v.x;
+        dst[1] = v.y;
+        dst[2] = v.z;
+    }
+}
+
+cudaError_t launch_pair_vertices(const ObjDesc* objs, const uint4* pairs, uint32_t pair_cap, const uint32_t* counters,
+                                 float* out, uint32_t out_cap_pairs, cudaStream_t s)
+{
+    if (out_cap_pairs == 0) return cudaSuccess;
+    const uint64_t work = (uint64_t)(pair_cap < out_cap_pairs ? pair_cap : out_cap_pairs) * 6u;
+    uint64_t blocks = (work + 255) / 256;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    pair_vertices_kernel<<<blocks ? (uint32_t)blocks : 1u, 256, 0, s>>>(objs, pairs, pair_cap, counters, out, out_cap_pairs);
+    return cudaGetLastError();
+}
+
+// =================================================================================================
+// Node-box wireframes: OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:69-124) + makeCube
+// (src/utils/utils.cpp:15-70). Node i contributes 8 corners and 12 edges (24 indices, offset by 8 i). The corner
+// arithmetic follows the reference literally: h = 0.5f * (max - min); corner = (+-h) + (min - (-h)) per axis.
+// =================================================================================================
+__global__ void __launch_bounds__(256) box_wireframe_kernel(const float* __restrict__ nodes, uint32_t n,
+                                                            float* __restrict__ verts, uint32_t* __restrict__ idx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2* p = reinterpret_cast<const float2*>(nodes) + 3ull * i;
+    const float2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
+    const float mn[3] = {a.x, a.y, b.x}, mx[3] = {b.y, c.x, c.y};
+    float h[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        h[k] = __fmul_rn(0.5f, __fsub_rn(mx[k], mn[k]));
+        d[k] = __fsub_rn(mn[k], -h[k]); // aabb.m_minimum - cubeVertices[4]
+    }
+    // makeCube corner signs: front quad z = +h (0..3), back quad z = -h (4..7); x: - + + -, y: - - + +
+    const float sx[4] = {-1.f, 1.f, 1.f, -1.f}, sy[4] = {-1.f, -1.f, 1.f, 1.f};
+    float* v = verts + 24ull * i;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        const float cx = sx[q & 3] < 0.f ? -h[0] : h[0];
+        const float cy = sy[q & 3] < 0.f ? -h[1] : h[1];
+        const float cz = q < 4 ? h[2] : -h[2];
+        v[3 * q] = __fadd_rn(cx, d[0]);
+        v[3 * q + 1] = __fadd_rn(cy, d[1]);
+        v[3 * q + 2] = __fadd_rn(cz, d[2]);
+    }
+    const uint32_t e[24] = {0, 1, 1, 2, 2, 3, 3, 0, 4, 5, 5, 6, 6, 7, 7, 4, 1, 5, 0, 4, 3, 7, 2, 6}; // utils.cpp:33-69
+    uint32_t* o = idx + 24ull * i;
+#pragma unroll
+    for (int q = 0; q < 24; q++) o[q] = e[q] + 8u * i;
+}
+
+cudaError_t launch_box_wireframe(const float* nodes, uint32_t n, float* verts, uint32_t* idx, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    box_wireframe_kernel<<<(n + 255) / 256, 256, 0, s>>>(nodes, n, verts, idx);
+    return cudaGetLastError();
+}
+
 cudaError_t collide_configure(int* grid_blocks)
 {
     cudaError_t e = cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes);

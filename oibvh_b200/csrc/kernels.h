@@ -117,4 +117,10 @@ cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj,
                            uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
                            uint32_t world, cudaStream_t s);
 
+// collided-triangle vertex stream (Scene::convertToVertexArray) and node-box wireframes
+// (OibvhTree::convertToVertexArray) as device-side gathers
+cudaError_t launch_pair_vertices(const ObjDesc* objs, const uint4* pairs, uint32_t pair_cap, const uint32_t* counters,
+                                 float* out, uint32_t out_cap_pairs, cudaStream_t s);
+cudaError_t launch_box_wireframe(const float* nodes, uint32_t n, float* verts, uint32_t* idx, cudaStream_t s);
+
 } // namespace oibvh

@@ -252,6 +252,9 @@ class Ref:
         L.ref_collide_detect.restype = C.c_uint32
         L.ref_collide_detect.argtypes = [vp]
         L.ref_collide_get_pairs.argtypes = [vp, u32p]
+        L.ref_collide_vertex_array.restype = C.c_uint32
+        L.ref_collide_vertex_array.argtypes = [vp, f32p]
+        L.ref_box_wireframe.argtypes = [f32p, C.c_uint32, f32p, u32p]
         L.ref_triangle_intersect.restype = C.c_int
         L.ref_triangle_intersect.argtypes = [f32p, f32p]
         L.ref_aabb_overlap.restype = C.c_int
@@ -356,6 +359,23 @@ class Ref:
             self.lib.ref_collide_get_pairs(c, out.ctypes.data_as(u32p))
         return out
 
+    def collide_vertex_array(self, c):
+        """unmodified SimpleCollide::convertToVertexArray after a detect: [pairs*6, 3]"""
+        n = self.lib.ref_collide_vertex_array(c, None)
+        out = np.empty((n, 3), np.float32)
+        if n:
+            self.lib.ref_collide_vertex_array(c, out.ctypes.data_as(f32p))
+        return out
+
+    def box_wireframe(self, nodes):
+        nodes, npx = _f32(np.asarray(nodes, np.float32).reshape(-1, 6))
+        n = len(nodes)
+        verts = np.empty((n * 8, 3), np.float32)
+        idx = np.empty(n * 24, np.uint32)
+        if n:
+            self.lib.ref_box_wireframe(npx, n, verts.ctypes.data_as(f32p), idx.ctypes.data_as(u32p))
+        return verts, idx
+
     # ---- free functions ----
     def tri_tri(self, p, q):
         p, pp = _f32(p)
@@ -386,6 +406,39 @@ class Ref:
         for m in ms:
             self.mesh_destroy(m)
         return pairs
+
+
+def pair_vertices(pairs, trees):
+    """Restates Scene::convertToVertexArray (src/cuda/scene.cu:68-93) == SimpleCollide::convertToVertexArray
+    (src/cpu/simpleCollide.cpp:191-216): pair i -> rows 6i..6i+5 = positions of triangle A's three vertices, then
+    triangle B's. pairs: [H,4] (bvhA, bvhB, triA, triB) with tri indexing trees[k] = (faces[T,3], pos[V,3])."""
+    p = np.asarray(pairs, np.uint32).reshape(-1, 4)
+    out = np.empty((len(p) * 6, 3), np.float32)
+    for i, (a, b, ta, tb) in enumerate(p):
+        fa, pa = trees[a]
+        fb, pb = trees[b]
+        out[6 * i:6 * i + 3] = pa[fa[ta]]
+        out[6 * i + 3:6 * i + 6] = pb[fb[tb]]
+    return out
+
+
+_CUBE_SIGNS = np.array([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1],
+                        [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1]], np.float32)  # utils.cpp:21-31
+_CUBE_EDGES = np.array([0, 1, 1, 2, 2, 3, 3, 0, 4, 5, 5, 6, 6, 7, 7, 4, 1, 5, 0, 4, 3, 7, 2, 6], np.uint32)  # utils.cpp:33-69
+
+
+def box_wireframe(nodes, max_nodes=256, n_prims=None):
+    """Restates OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:69-124) + makeCube (src/utils/utils.cpp:15-70)
+    in fp32: boxes of the first min(internal, max_nodes) nodes; h = 0.5f * (max - min); corner = (+-h) + (min - (-h))."""
+    nodes = np.asarray(nodes, np.float32).reshape(-1, 6)
+    internal = len(nodes) - n_prims if n_prims is not None else len(nodes)
+    n = min(internal, max_nodes)
+    mn, mx = nodes[:n, :3], nodes[:n, 3:]
+    h = (np.float32(0.5) * (mx - mn)).astype(np.float32)
+    diff = (mn - (-h)).astype(np.float32)                       # aabb.m_minimum - cubeVertices[4]
+    verts = (_CUBE_SIGNS[None, :, :] * h[:, None, :]).astype(np.float32) + diff[:, None, :]
+    idx = (_CUBE_EDGES[None, :] + (np.arange(n, dtype=np.uint32) * 8)[:, None]).astype(np.uint32)
+    return verts.reshape(-1, 3).astype(np.float32), idx.reshape(-1)
 
 
 def canonical_pairs(pairs, perms=None):

@@ -252,6 +252,41 @@ extern "C"
             std::memcpy(out4, col.m_intTriPairs.data(), col.m_intTriPairs.size() * sizeof(int_tri_pair_node_t));
     }
 
+    // SimpleCollide::convertToVertexArray (src/cpu/simpleCollide.cpp:191-216): six vec3 per intersecting pair
+    uint32_t ref_collide_vertex_array(void* c, float* out /* pairs * 18 */)
+    {
+        auto& col = *static_cast<RefCollide*>(c)->collide;
+        col.convertToVertexArray();
+        static_assert(sizeof(glm::vec3) == 12, "vec3 is three packed floats");
+        if (out && !col.m_vertices.empty())
+            std::memcpy(out, col.m_vertices.data(), col.m_vertices.size() * sizeof(glm::vec3));
+        return (uint32_t)col.m_vertices.size();
+    }
+    // Node-box wireframes: the loop body of OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:80-113; that file
+    // is CUDA host code and is not compiled here) around the UNMODIFIED makeCube (src/utils/utils.cpp:15-70).
+    void ref_box_wireframe(const float* nodes6, uint32_t n, float* verts /* n*24 */, uint32_t* idx /* n*24 */)
+    {
+        for (uint32_t i = 0; i < n; i++)
+        {
+            aabb_box_t aabb;
+            aabb.m_minimum = glm::vec3(nodes6[6 * i], nodes6[6 * i + 1], nodes6[6 * i + 2]);
+            aabb.m_maximum = glm::vec3(nodes6[6 * i + 3], nodes6[6 * i + 4], nodes6[6 * i + 5]);
+            std::vector<glm::vec3> cubeVertices;
+            std::vector<unsigned int> cubeIndices;
+            makeCube(0.5f * (aabb.m_maximum.x - aabb.m_minimum.x), 0.5f * (aabb.m_maximum.y - aabb.m_minimum.y),
+                     0.5 * (aabb.m_maximum.z - aabb.m_minimum.z), cubeVertices, cubeIndices);
+            const glm::vec3 diff = aabb.m_minimum - cubeVertices[4];
+            for (size_t k = 0; k < cubeVertices.size(); k++)
+            {
+                const glm::vec3 pos = cubeVertices[k] + diff;
+                verts[24 * i + 3 * k] = pos.x;
+                verts[24 * i + 3 * k + 1] = pos.y;
+                verts[24 * i + 3 * k + 2] = pos.z;
+            }
+            for (size_t j = 0; j < cubeIndices.size(); j++) idx[24 * i + j] = cubeIndices[j] + (unsigned)cubeVertices.size() * i;
+        }
+    }
+
     // ---- free functions ------------------------------------------------------------------------
     // src/utils/utils.cpp:97-169
     int ref_triangle_intersect(const float* p /*3x3*/, const float* q /*3x3*/)

@@ -57,3 +57,15 @@ def test_transforms(port, golden):
         assert_bit_equal(cur, g[f"pos{i + 1}"], f"step {i}")
         i += 1
     assert i == 5
+
+
+def test_vertex_streams(golden):
+    """pair vertex stream (SimpleCollide::convertToVertexArray) and node-box wireframes (makeCube) restatements"""
+    g = golden["vertex_streams"]
+    trees = [(g["faces"], g["pos"]), (g["faces"], g["posB"])]
+    assert_bit_equal(oracle.pair_vertices(g["pairs"], trees), g["pair_vertices"], "pair vertices")
+    assert len(g["pair_vertices"]) == 6 * len(g["pairs"]) > 0
+    v, i = oracle.box_wireframe(g["nodesA"], 256, n_prims=len(g["faces"]))
+    assert_bit_equal(v, g["box_vertices"], "box corners")
+    assert np.array_equal(i, g["box_indices"])
+    assert len(i) == 24 * 256

@@ -102,3 +102,28 @@ def test_transform_equals_mesh_transform(port, ref):
         cur = port.transform_positions(cur, M)
         assert_bit_equal(cur, ref.mesh_positions(m, len(pos)), "rotated positions")
     ref.mesh_destroy(m)
+
+
+def test_vertex_streams_equal_reference(port, ref):
+    """oracle.pair_vertices / box_wireframe == unmodified SimpleCollide::convertToVertexArray / makeCube"""
+    pos, faces = meshgen.blob(24, 16, seed=5)
+    posB = (pos + np.float32([0.9, 0.1, 0.05])).astype(np.float32)
+    ms = [ref.mesh_create(pos, faces), ref.mesh_create(posB, faces)]
+    bs = [ref.bvh_create(m) for m in ms]
+    col = ref.collide_create()
+    for b in bs:
+        ref.bvh_build(b)
+        ref.collide_add(col, b)
+    pairs = ref.collide_detect(col)
+    assert len(pairs) > 50
+    assert_bit_equal(oracle.pair_vertices(pairs, [(faces, pos), (faces, posB)]), ref.collide_vertex_array(col), "verts")
+    aabbs, _ = ref.bvh_dump_bfs(bs[0])
+    v1, i1 = ref.box_wireframe(aabbs[:256])
+    v2, i2 = oracle.box_wireframe(aabbs, 256, n_prims=len(faces))
+    assert_bit_equal(v2, v1, "box corners")
+    assert np.array_equal(i1, i2)
+    ref.collide_destroy(col)
+    for b in bs:
+        ref.bvh_destroy(b)
+    for m in ms:
+        ref.mesh_destroy(m)

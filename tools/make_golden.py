@@ -5,7 +5,8 @@ The fixtures freeze, for seeded inputs:
   * SimpleBVH node AABBs in BFS order (== oibvh array order) for several primitive counts,
   * SimpleCollide::detect pair sets (bvhA, bvhB, faceA, faceB) for two- and three-body scenes,
   * triangleIntersect verdicts for random / touching / degenerate triangle pairs,
-  * glm translate / rotate matrices and Mesh::transform results, Mesh::m_aabb and m_center.
+  * glm translate / rotate matrices and Mesh::transform results, Mesh::m_aabb and m_center,
+  * SimpleCollide::convertToVertexArray vertex streams and makeCube node-box wireframes.
 The reference's GPU path cannot run here (no GPU in the container) and ships no fixtures of its own
 (SURVEY.md §4), so these are the known answers every parity test is anchored to.
 """
@@ -39,10 +40,40 @@ def tri_cases(rng, n):
     return p.reshape(n, 9), q.reshape(n, 9)
 
 
+def vertex_streams(R):
+    """SimpleCollide::convertToVertexArray output (in the reference's own pair order) and node-box wireframes
+    (unmodified makeCube) for a small two-body scene -> tests/golden/vertex_streams.npz"""
+    P = oracle.Port()
+    spos, sfaces = P.gen_uv_sphere(16)
+    mA, mB = R.mesh_create(spos, sfaces), R.mesh_create(spos, sfaces)
+    R.mesh_translate(mB, (1.0, 0.1, 0.05))
+    posB = R.mesh_positions(mB, len(spos))
+    bA, bB = R.bvh_create(mA), R.bvh_create(mB)
+    R.bvh_build(bA)
+    R.bvh_build(bB)
+    c = R.collide_create()
+    R.collide_add(c, bA)
+    R.collide_add(c, bB)
+    pairs = R.collide_detect(c)
+    verts = R.collide_vertex_array(c)
+    aabbs, _ = R.bvh_dump_bfs(bA)
+    box_v, box_i = R.box_wireframe(aabbs[:256])
+    np.savez_compressed(os.path.join(OUT, "vertex_streams.npz"), pos=spos, faces=sfaces, posB=posB, pairs=pairs,
+                        pair_vertices=verts, nodesA=aabbs, box_vertices=box_v, box_indices=box_i)
+    R.collide_destroy(c)
+    for h in (bA, bB):
+        R.bvh_destroy(h)
+    for h in (mA, mB):
+        R.mesh_destroy(h)
+
+
 def main():
     assert oracle.ref_available(), "build oracle/_ref first: make -C oracle ref"
     R = oracle.Ref()
     os.makedirs(OUT, exist_ok=True)
+    if "--vertex-streams-only" in sys.argv:
+        vertex_streams(R)
+        return
     rng = np.random.default_rng(20240917)
 
     # ---- trees ----
@@ -136,6 +167,7 @@ def main():
         xf[f"center{i + 1}"] = R.mesh_center(m)
     xf["steps"] = np.array([repr(s) for s in steps])
     np.savez_compressed(os.path.join(OUT, "transforms.npz"), **xf)
+    vertex_streams(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
