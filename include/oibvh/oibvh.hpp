@@ -253,7 +253,7 @@ public:
     OibvhTree(const OibvhTree&) = delete;
     OibvhTree& operator=(const OibvhTree&) = delete;
 
-    explicit OibvhTree(const std::shared_ptr<Mesh> mesh) : m_mesh(mesh), m_buildDone(false)
+    explicit OibvhTree(const std::shared_ptr<Mesh> mesh) : m_buildDone(false), m_mesh(mesh)
     {
         std::vector<float> pos = packedPositions();
         const float aabb[6] = {mesh->m_aabb.m_minimum.x, mesh->m_aabb.m_minimum.y, mesh->m_aabb.m_minimum.z,
@@ -263,7 +263,7 @@ public:
     }
     // copy constructor of the reference (src/cuda/oibvhTree.cu:17-33): same Morton order / tree as `other`
     OibvhTree(const std::shared_ptr<OibvhTree> other, const std::shared_ptr<Mesh> mesh)
-        : m_mesh(mesh), m_buildDone(other->m_buildDone)
+        : m_buildDone(other->m_buildDone), m_mesh(mesh)
     {
         oibvh_detail::check(oibvh_tree_clone(other->m_handle, &m_handle));
     }
@@ -311,6 +311,7 @@ public:
         for (uint32_t i = 0; i < V; i++) m_positions[i] = oibvh_math::vec3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
     }
     oibvh_tree* handle() const { return m_handle; }
+    const std::shared_ptr<Mesh>& mesh() const { return m_mesh; } // extension: the mesh this tree was created on
 
     // Many-body extensions (the reference loops over its objects, one build / refit call each): every tree of up to
     // 4096 triangles is processed by one thread block of ONE launch. Results equal the per-tree calls.

@@ -4,7 +4,7 @@
  * This is the drop-in boundary: plain pointers and sizes, opaque handles, int status codes. The reference
  * (hhhcbw/oibvh) has no FFI layer -- its host classes launch kernels inline -- so each entry point below names
  * the reference host method it replaces (paths relative to the reference checkout). The C++ facade in
- * include/oibvh/*.hpp re-creates the reference's classes (Mesh, OibvhTree, Scene, DeviceType, aabb_box_t,
+ * include/oibvh/ (oibvh.hpp, model.hpp) re-creates the reference's classes (Mesh, OibvhTree, Scene, DeviceType, aabb_box_t,
  * int_tri_pair_node_t) on top of exactly these calls; INTEGRATION.md shows the binding.
  *
  * Conventions
