@@ -136,6 +136,96 @@ def cpu_baseline_port(pos, faces, posB, aabb, frames=3):
                       "(the reference CPU path is single-threaded)", "pairs": ms[0][1], "candidates": ms[0][2]}
 
 
+REF_GPU_EXE = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
+REF_GPU_NU, REF_GPU_NV = 256, 192
+
+
+def ours_frame_ms(ob, ctx, stream, pos, faces, frames=30):
+    """this library's frame (same stages as the main workload, graph replay) on arbitrary meshes: used to put a number
+    beside the reference GPU path on the bounded sample it can run"""
+    import torch
+    mesh_a = ob.Mesh(pos, faces)
+    mesh_b = mesh_a.copy()
+    ta = ob.OibvhTree(mesh_a, ctx=ctx)
+    ta.build()
+    tb = ob.OibvhTree(ta, mesh_b)
+    M0 = mesh_b.transform_matrix_translate(OFFSET_B)
+    mesh_b.transform(M0)
+    tb.transform(M0)
+    M_rot = mesh_b.transform_matrix_rotate((0.0, 0.0, 1.0), 1.0)
+    tb.build()
+    sc = ob.Scene(ctx)
+    sc.addOibvhTree(ta)
+    sc.addOibvhTree(tb)
+
+    def frame():
+        ob.build_many([ta, tb])
+        tb.transform(M_rot)
+        ob.refit_many([ta, tb])
+        sc.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
+    for _ in range(3):
+        frame()
+        sc.counts()
+    ctx.capture_begin()
+    frame()
+    g = ctx.capture_end()
+    g.launch()
+    sc.counts()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(frames):
+        g.launch()
+    e1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    n_pairs, _ = sc.counts()
+    g.close()
+    sc.close()
+    for t in (ta, tb):
+        t.close()
+    return {"value": e0.elapsed_time(e1) / frames, "unit": UNIT, "pairs_last_frame": int(n_pairs),
+            "timing": "CUDA events around graph replays, inputs resident (the reference's figure includes its own "
+                      "host<->device copies, which are part of its API)"}
+
+
+
+
+def reference_gpu_baseline(pos, faces, frames=12, keep=None):
+    """The UNMODIFIED reference GPU path (its five .cu files recompiled for sm_100a by `make -C oracle refgpu`,
+    driven by oracle/ref_gpu_main.cu) on the same meshes and the same frame, on this GPU: the recompiled kernels
+    this library replaces. A reported baseline like cpu_baseline -- never on the product path. Returns None when the
+    binary was not prebuilt (it needs /root/reference at build time)."""
+    import subprocess
+    import tempfile
+    if not os.path.exists(REF_GPU_EXE):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        mesh, out = os.path.join(d, "mesh.bin"), os.path.join(d, "pairs.bin")
+        with open(mesh, "wb") as f:
+            f.write(np.array([len(pos), len(faces)], np.uint32).tobytes())
+            f.write(np.ascontiguousarray(pos, np.float32).tobytes())
+            f.write(np.ascontiguousarray(faces, np.uint32).tobytes())
+            f.write(np.array(list(OFFSET_B) + [0.0, 0.0, 1.0, 1.0], np.float32).tobytes())
+        try:
+            res = subprocess.run([REF_GPU_EXE, mesh, str(frames), out], capture_output=True, text=True, timeout=60)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": "reference GPU path timed out"}
+        if res.returncode != 0:
+            return {"unavailable": f"reference GPU path failed (rc {res.returncode}): {res.stderr.strip()[:200]}"}
+        rows = np.array([[float(x) for x in l.split()[2:]] for l in res.stdout.splitlines() if l.startswith("frame")])
+        if keep is not None:
+            keep["pairs"] = np.fromfile(out, np.uint32).reshape(-1, 8)
+            keep["posB"] = np.fromfile(out + ".posB", np.float32).reshape(-1, 3)
+    rows = rows[min(2, len(rows) - 1):]  # the first frames pay allocations inside thrust
+    med = np.median(rows, axis=0)
+    return {"value": float(med[3]), "unit": UNIT, "kind": "reference GPU path (unmodified src/cuda/*.cu, nvcc sm_100a)",
+            "stage_ms": {"build": float(med[0]), "refit": float(med[1]), "detect": float(med[2])},
+            "pairs": int(rows[-1][4]), "frames": int(len(rows)),
+            "timing": "host clock around the reference's own synchronous calls (it copies trees, faces and vertices "
+                      "host<->device inside every build/refit/detect): build A + build B, rotate B + refit A + refit B, "
+                      "detectCollision(GPU0, 4, 3)"}
+
+
 def run_reference_arm(args):
     """The reference's own CPU implementation: unmodified SimpleBVH::build/refit + SimpleCollide::detect
     (oracle/_ref, compiled from /root/reference by oracle/Makefile). Single-threaded like the reference."""
@@ -371,6 +461,9 @@ def run_gpu_arm(args):
         scene.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
         if prefetch is not None:
             e2e_upload(prefetch)  # double buffering: the next step's H2D runs under this step's kernels
+        if dist is None:
+            # one C-ABI call: waits for the frame, reads the counters, copies the pair list into the pinned buffer
+            return scene.get_pairs_into(pair_host.data_ptr())
         n, _ = scene.counts()  # D2H of the counters (sync)
         ptr, n = scene.device_pairs()
         local = obd.pairs_tensor_from_device_ptr(ptr, n, torch.device("cuda", dev))
@@ -472,6 +565,18 @@ def run_gpu_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             posB = tree_b.m_positions
             line["cpu_baseline"] = cpu_baseline_port(pos, faces, posB, mesh_a.m_aabb)
+            # The unmodified reference GPU path only completes this scene up to ~10^5 triangles per body: it emits
+            # BVTT children untested, so at 2 x 196 608 triangles its front outgrows its fixed 10 M-node buffers and
+            # its unchecked level loop never terminates (measured on B200). Bounded sample: 2 x 98 304 triangles, with
+            # this library timed on the very same meshes beside it.
+            s_pos, s_faces = make_meshes(REF_GPU_NU, REF_GPU_NV)
+            ref_gpu = reference_gpu_baseline(s_pos, s_faces)
+            if ref_gpu is not None:
+                ref_gpu["sample"] = (f"2 x {len(s_faces)} triangles (largest size of this scene the reference GPU path "
+                                     "completes; it overflows its fixed 10M-node BVTT buffers at 2 x 196608)")
+                if "unavailable" not in ref_gpu:
+                    ref_gpu["ours_same_sample"] = ours_frame_ms(ob, ctx, stream, s_pos, s_faces)
+                line["reference_gpu"] = ref_gpu
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

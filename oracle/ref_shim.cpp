@@ -67,12 +67,14 @@ PFNGLVERTEXATTRIBPOINTERPROC glad_glVertexAttribPointer = nop_vap;
 void Shader::setInt(const std::string&, int) const {}
 void Shader::setBool(const std::string&, bool) const {}
 
+#ifndef REF_SHIM_DEVICE_TRANSFORM // the GPU build (oracle/ref_gpu_main.cu) links the reference's own transform.cu
 Transform::Transform() : m_deviceVec4s(nullptr) {}
 Transform::~Transform() {}
 void Transform::transformVec4(std::vector<glm::vec4>& vec4s, const glm::mat4 transformMat)
 {
     for (auto& v : vec4s) v = transformMat * v;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // (2) C wrapper
