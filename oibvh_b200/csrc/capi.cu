@@ -69,6 +69,7 @@ struct oibvh_ctx
     bool capturing = false;
     uint64_t capture_launches = 0;
     int collide_grid = 0;    // CTAs of the persistent detection kernel (cooperative launch)
+    uint32_t dense_seed_level = 8; // two-body scenes: level tested densely in round 0 (OIBVH_DENSE_SEED_LEVEL, 0 = off)
     uint64_t generation = 0; // bumped whenever device buffers referenced by enqueued work are reallocated
     std::vector<StageEvent> events;
     float stage_ms[OIBVH_STAGE_COUNT] = {0, 0, 0, 0};
@@ -376,6 +377,11 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = tree_emit_configure();
     if (e == cudaSuccess) e = collide_configure(&c->collide_grid);
+    if (const char* env = getenv("OIBVH_DENSE_SEED_LEVEL")) // tuning knob: 0 disables the dense round 0
+    {
+        const long v = strtol(env, nullptr, 10);
+        c->dense_seed_level = v <= 0 ? 1000u : (uint32_t)std::min<long>(std::max<long>(v, 6), 9);
+    }
     if (e == cudaSuccess) e = coop_sort_configure();
     if (e == cudaSuccess) e = small_trees_configure();
     if (e != cudaSuccess)
@@ -884,14 +890,21 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     StageScope scope(ctx, OIBVH_STAGE_BUILD);
     cudaStream_t s = ctx->stream;
     uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
+    // the key kernels of different trees are independent and latency-bound (random vertex gathers): odd trees go to
+    // the auxiliary stream like the emit kernels below
+    CU(cudaEventRecord(ctx->ev_fork, s));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (uint32_t i = 0; i < n; i++)
     {
         oibvh_tree* t = trees[i];
-        CU(cudaMemsetAsync(t->sort_ctl, 0, 64 * sizeof(uint32_t), s));
-        CU(launch_morton_hist(t->faces_in, t->pos, t->T, t->mesh, t->keys_a, nullptr, s));
+        cudaStream_t st = (i & 1) ? ctx->aux_stream : s;
+        CU(cudaMemsetAsync(t->sort_ctl, 0, 64 * sizeof(uint32_t), st));
+        CU(launch_morton_hist(t->faces_in, t->pos, t->T, t->mesh, t->keys_a, nullptr, st));
         count_launch(ctx);
         ka[i] = t->keys_a; kb[i] = t->keys_b; va[i] = t->vals_a; vb[i] = t->vals_b; ctl[i] = t->sort_ctl; T[i] = t->T;
     }
+    CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     cudaError_t e = launch_coop_sort_many(n, ka, kb, va, vb, T, ctl, s);
     if (e == cudaErrorInvalidValue)
     {
@@ -1280,6 +1293,10 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     {
         expand_levels = 3;
         k0 = maxL <= 5 ? maxL : 3 + (maxL - 3) % 3;
+        // two-body scenes skip the first latency-bound rounds: all node pairs of level k0 are tested directly by
+        // the whole grid (dense_seed_phase); k0 keeps (maxL - k0) a multiple of 3
+        if (n_obj == 2 && maxL >= ctx->dense_seed_level + 3)
+            k0 = ctx->dense_seed_level + (maxL - ctx->dense_seed_level) % 3;
     }
     else
     {

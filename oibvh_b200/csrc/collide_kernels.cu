@@ -384,6 +384,84 @@ __device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32
     flush(true);
 }
 
+// Dense round 0 for scenes of very few objects (two-body scenes): instead of walking down from the root pair through
+// several latency-bound rounds of a handful of items (each costs a grid barrier plus ~4 dependent L2 round trips,
+// ~4.5 us, whatever its size), ALL node pairs (a, b) at level `k0` of an object pair are tested directly, spread over
+// every warp of the grid: 4^8 = 65 K .. 4^11 = 4 M box tests are less work than the rounds they replace. A level is a
+// contiguous slice, so a warp's 32 consecutive combinations read one broadcast box of A and 32 consecutive boxes of B.
+// Same emission path (per-warp staging, one atomic per flush) and the same shard rule as expand_phase.
+__device__ void dense_seed_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32_t* s_lv,
+                                 const ObjDesc* __restrict__ objs, uint4* out, uint32_t front_cap, uint4* cand,
+                                 uint32_t cand_cap, uint32_t* counters, uint32_t n_pairs, uint32_t k0, uint32_t rank,
+                                 uint32_t world, uint32_t n_obj)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t* next_count = counters + CTR_FRONT0 + 1;
+    const uint32_t total_warps = gridDim.x * kColWarps;
+    constexpr uint32_t kHalf = kStageCap / 2;
+    uint4* stage = s_stage + warp * kStageCap;
+    uint32_t staged = 0; // warp-uniform; one kind per object pair (flushed before the kind can change)
+    auto flush = [&](bool is_cand) {
+        if (staged == 0) return;
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(is_cand ? counters + CTR_CANDIDATES : next_count, staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint4* dst = is_cand ? cand : out;
+        const uint32_t cap = is_cand ? cand_cap : front_cap;
+        if (base + staged > cap && lane == 0) atomicOr(counters + CTR_OVERFLOW, is_cand ? 2u : 1u);
+        for (uint32_t j = lane; j < staged; j += 32)
+            if (base + j < cap) dst[base + j] = stage[j];
+        __syncwarp();
+        staged = 0;
+    };
+    const uint32_t gw = blockIdx.x * kColWarps + warp;
+    for (uint32_t p = 0; p < n_pairs; p++)
+    {
+        const uint4 it = seed_entry(n_obj, p);
+        const ObjDesc A = get_obj(s_objs, objs, it.x), B = get_obj(s_objs, objs, it.y);
+        const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
+        const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
+        const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
+        if (!box_overlap(load_box(nodesA, 0), load_box(nodesB, 0))) continue; // disjoint roots (warp-uniform)
+        const uint32_t ka = min(k0, A.L), kb = min(k0, B.L);
+        const uint32_t nA = va.count(ka), nB = vb.count(kb), baseA = va.offset(ka), baseB = vb.offset(kb);
+        const bool to_cand = (ka == A.L) && (kb == B.L);
+        const uint32_t za = to_cand ? 0u : (ka << kNodeLevelShift), zb = to_cand ? 0u : (kb << kNodeLevelShift);
+        const uint32_t total = nA * nB; // <= 4^11
+        for (uint32_t c0 = gw * 64; c0 < total; c0 += total_warps * 64)
+        {
+            const uint32_t c[2] = {c0 + lane, c0 + 32 + lane};
+            bool hit[2];
+            uint32_t ia[2], ib[2];
+            Box a[2], b[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+            {
+                hit[u] = c[u] < total && (world == 1 || ((p + c[u]) % world) == rank);
+                ia[u] = c[u] / nB;
+                ib[u] = c[u] - ia[u] * nB;
+                if (hit[u])
+                {
+                    a[u] = load_box(nodesA, baseA + ia[u]);
+                    b[u] = load_box(nodesB, baseB + ib[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (hit[u]) hit[u] = box_overlap(a[u], b[u]);
+            const uint32_t mask0 = __ballot_sync(0xffffffffu, hit[0]), mask1 = __ballot_sync(0xffffffffu, hit[1]);
+            const uint32_t cnt0 = __popc(mask0), cnt = cnt0 + __popc(mask1);
+            if (cnt == 0) continue; // warp-uniform
+            if (staged + cnt > kHalf) flush(to_cand);
+            if (hit[0]) stage[staged + __popc(mask0 & lanemask_lt())] = make_uint4(it.x, it.y, za + ia[0], zb + ib[0]);
+            if (hit[1]) stage[staged + cnt0 + __popc(mask1 & lanemask_lt())] = make_uint4(it.x, it.y, za + ia[1], zb + ib[1]);
+            staged += cnt;
+        }
+        flush(to_cand);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Narrow phase: separating-axis test, literal operation order of the reference CPU code, IEEE fp32 with
 // explicit round-to-nearest intrinsics (nvcc would otherwise contract a*b - c*d into FMAs and flip
@@ -560,8 +638,12 @@ __global__ void __launch_bounds__(kColThreads, 1)
         uint4* out = (r & 1) ? front0 : front1;
         if (r == 0 && computed_seeds) in = nullptr;
         const uint32_t k = r == 0 ? levels0 : levels; // schedule chosen by the host (see scene_enqueue)
-        expand_phase(s_stage, s_objs, s_lv, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size, k, rank,
-                     world, n_obj);
+        if (r == 0 && computed_seeds && k > kMaxExpandLevels)
+            dense_seed_phase(s_stage, s_objs, s_lv, objs, out, front_cap, cand, cand_cap, counters, front_size, k, rank,
+                             world, n_obj);
+        else
+            expand_phase(s_stage, s_objs, s_lv, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size, k,
+                         rank, world, n_obj);
         front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0 + r + 1);
         stamp(gen);
     }

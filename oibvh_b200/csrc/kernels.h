@@ -95,6 +95,11 @@ struct ObjDesc
 constexpr int kNodeLevelShift = 26;
 constexpr uint32_t kNodePosMask = (1u << kNodeLevelShift) - 1;
 
+// a BVTT round descends at most this many levels per side (4^5 = 1024 combinations per node pair); a larger first-round
+// value selects the dense level-k0 seeding of scenes with very few objects (collide_kernels.cu: dense_seed_phase)
+constexpr uint32_t kMaxExpandLevels = 5;
+constexpr uint32_t kMaxDenseSeedLevel = 11;
+
 // counters block in device memory (uint32 each)
 enum
 {
