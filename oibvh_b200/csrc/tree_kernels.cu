@@ -502,6 +502,28 @@ __device__ __forceinline__ void box_floats(const Box& b, float* f)
     f[0] = b.lx; f[1] = b.ly; f[2] = b.lz; f[3] = b.hx; f[4] = b.hy; f[5] = b.hz;
 }
 
+#ifdef OIBVH_PROFILE
+// phase stamps of warp 1 / lane 0 of every CTA (ns, %globaltimer): [0] entry, [1] faces arrived, [2] vertices arrived,
+// [3] heights 0..2 staged and bulk stores issued, [4] heights 3..7 done, [5] bulk stores have read shared memory
+__device__ unsigned long long g_emit_phase[4096][8];
+__device__ __forceinline__ void phase_stamp(int k, uint32_t consume, bool on)
+{
+    __shared__ uint32_t s_prof_scratch[32];
+    if (!on) return;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_prof_scratch + (k & 31))), "r"(consume) : "memory");
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    if (blockIdx.x < 4096) g_emit_phase[blockIdx.x][k] = t;
+}
+extern "C" int oibvh_debug_emit_phases(unsigned long long* out /* 4096*8 */)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_emit_phase, sizeof(g_emit_phase));
+}
+#define PHASE_STAMP(k, x) phase_stamp(k, (uint32_t)(x), lane == 0 && ((warp_leaf0 / kWarpLeaves) % kEmitWarps) == 1)
+#else
+#define PHASE_STAMP(k, x)
+#endif
+
 // One warp's 128 leaves: faces -> leaf boxes -> heights 1..7, all stored. FULL = every leaf of the chunk exists
 // (compile-time true folds every bounds predicate away; the partial last chunk takes the generic instantiation).
 // Returns the warp root (height 7) in lane 0.
@@ -513,6 +535,7 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
 {
     const uint32_t leaf0 = warp_leaf0 + lane * kLeavesPerThread;
     auto in = [&](uint32_t i) { return FULL || i < T; };
+    PHASE_STAMP(0, lane);
     // ---- faces of this thread's 4 consecutive leaves ----
     uint32_t idx[12];
     const bool full = FULL || leaf0 + 4 <= T;
@@ -566,10 +589,12 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
         }
     }
 
+    PHASE_STAMP(1, idx[11]);
     // ---- heights 0..2 in registers. A node at height h, position p exists iff p * 2^h < T. ----
     float4 v[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) v[k] = __ldg(pos4 + idx[k]); // idx = 0 for missing leaves: harmless load
+    PHASE_STAMP(2, __float_as_uint(v[11].x) ^ __float_as_uint(v[5].y) ^ __float_as_uint(v[0].z));
     Box leaf[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) leaf[k] = box_of(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
@@ -602,6 +627,7 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
         st2[m2 + lane * 3 + 2] = make_float2(cur.hy, cur.hz);
         fence_proxy_async_smem(); // generic-proxy writes above -> visible to the async proxy
         __syncwarp();
+#ifndef OIBVH_EXP_NOSTORE // timing diagnostic only: skip the bulk stores of heights 0..2 (87.5 % of the written bytes)
         if (lane == 0)
         {
             slice_store(g0, st0, 3072, m0);
@@ -609,6 +635,7 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
             slice_store(g2, st2, 768, m2);
             bulk_commit();
         }
+#endif
     }
     else
     {
@@ -632,6 +659,7 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
             warp_copy_out(nodes + 3ull * (lv.off[L - 2] + (warp_leaf0 >> 2)), wsm + 3 * 64, 3 * ((warp_valid + 3) >> 2),
                           lane);
     }
+    PHASE_STAMP(3, __float_as_uint(cur.lx));
 #pragma unroll
     for (int h = 3; h <= kWarpLevels; h++)
     {
@@ -642,7 +670,9 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
         if ((lane & (2 * delta - 1)) == 0 && in(leaf0) && (FULL || (uint32_t)h <= L))
             store_box(nodes, lv.off[L - h] + (leaf0 >> h), cur);
     }
+    PHASE_STAMP(4, __float_as_uint(cur.hx));
     if (FULL && lane == 0) bulk_wait_read(); // the staging areas may be reused / released after this
+    PHASE_STAMP(5, lane);
     return cur;
 }
 
@@ -654,20 +684,128 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
 #endif
 // measured on B200: refit is fastest at 64 registers (4 CTAs/SM, no spills), build (one more gather level in
 // flight) at 85 registers (3 CTAs/SM); 48 registers / 5 CTAs spills and loses 15-25 %
+// Largest number of chunks whose upper levels go to the finisher CTA: one CTA of 8 warps handles a group of 32 chunks in
+// ~2 dependent L2 round trips, which keeps pace with up to a few thousand chunks; beyond that (measured at 16 392
+// chunks: 285 vs 251 us) the distributed scheme below (the last arriver of a group reduces it) scales better and its
+// tail no longer matters.
+#ifndef OIBVH_EMIT_FINISHER_MAX_CHUNKS
+#define OIBVH_EMIT_FINISHER_MAX_CHUNKS 4096
+#endif
+// Levels above the chunk roots, done by ONE extra "finisher" CTA of the same launch (block 0).
+// A chunk CTA only publishes: the lane that stored the chunk root adds 1 to the arrival counter of its group of 32
+// chunks with a release-RED (fire and forget: no return value to wait for, the warp exits, the CTA slot is free for the
+// next chunk). The finisher's warps poll the group counters (acquire), reduce every completed group of 32 nodes by
+// shuffles (5 levels), and walk the remaining stages inside the CTA (CTA barrier between stages). Measured at
+// T = 2^20 against the previous scheme (every CTA's warp 0: fence + atomicAdd with return, the last arriver of a group
+// reduces it and arrives one stage up): a chunk CTA held its slot a median 1.5 us after its chunk was done, and the
+// launch ended 4.5 us after the last chunk (two dependent fence/atomic/load stages).
+constexpr uint32_t kFinisherSmemNodes = 512; // stage results handed to the next stage through shared memory
+__device__ __noinline__ void emit_finisher(float2* __restrict__ nodes, uint32_t L, const LevelTable& lv, uint32_t* ctr,
+                                              float2* scratch /* the CTA's (otherwise unused) staging area */)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t level = L - kChunkLevels; // level of the completed nodes that feed this stage
+    bool first_stage = true;
+    const float2* buf_in = nullptr;    // null: inputs come from global memory (stage 1: written by the chunk CTAs)
+    float2* buf_out = scratch;
+    while (level > 0)
+    {
+        const uint32_t n = lv.cnt[level];
+        const uint32_t groups = (n + 31) >> 5;
+        const uint32_t next_level = level > 5 ? level - 5 : 0;
+        // a stage's outputs (one node per group, level - 5) stay in shared memory for the next stage: no L2 round trip
+        const bool out_smem = next_level > 0 && groups <= kFinisherSmemNodes;
+        for (uint32_t g = warp; g < groups; g += kEmitWarps)
+        {
+            const uint32_t first = g << 5;
+            const uint32_t members = min(32u, n - first);
+            if (first_stage)
+            {
+                if (lane == 0)
+                {
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(ctr + g) < members)
+                        if (++spins > (1u << 25)) __trap(); // a chunk CTA never arrived: fail the launch loudly
+                    ctr[g] = 0; // every member has arrived: re-arm for the next launch on this tree
+                }
+                __syncwarp();
+            }
+            Box cur = Box{0, 0, 0, 0, 0, 0};
+            if (lane < members)
+                cur = buf_in ? unstage_box(buf_in, first + lane) : load_box_cg(nodes, lv.off[level] + first + lane);
+            uint32_t l = level;
+#pragma unroll
+            for (int s5 = 0; s5 < 5; s5++)
+            {
+                if (l == 0) break; // warp-uniform
+                const Box right = shfl_down_box(cur, 1 << s5);
+                const uint32_t child = (first >> s5) + (lane >> s5); // position at level l of this lane's node
+                const bool owner = (lane & ((2u << s5) - 1)) == 0;
+                if (owner && child < lv.cnt[l])
+                {
+                    if (child + 1 < lv.cnt[l]) cur = box_merge(cur, right);
+                    store_box(nodes, lv.off[l - 1] + (child >> 1), cur);
+                }
+                l--;
+            }
+            if (out_smem && lane == 0) stage_box(buf_out, g, cur); // lane 0 holds node g of level - 5
+        }
+        __syncthreads(); // this stage's nodes are visible to the CTA's warps (shared memory, or global via ld.cg)
+        buf_in = out_smem ? buf_out : nullptr;
+        buf_out = (buf_out == scratch) ? scratch + 3 * kFinisherSmemNodes : scratch;
+        level = next_level;
+        first_stage = false;
+    }
+}
+
+#ifdef OIBVH_PROFILE
+// per-CTA wall-clock stamps (ns, %globaltimer): [0] CTA start, [1] warp 1 past the chunk, [2] warp 0 before the
+// top-of-tree stages, [3] warp 0 done
+__device__ unsigned long long g_emit_prof[4096][4];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define EMIT_STAMP(slot, cond)                                                                                     \
+    do                                                                                                             \
+    {                                                                                                              \
+        if ((cond) && blockIdx.x < 4096) g_emit_prof[blockIdx.x][slot] = gtime();                                  \
+    } while (0)
+extern "C" int oibvh_debug_emit_profile(unsigned long long* out /* 4096*4 */)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_emit_prof, sizeof(g_emit_prof));
+}
+#else
+#define EMIT_STAMP(slot, cond)
+#endif
+
 template <bool BUILD>
 __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : OIBVH_EMIT_MINB)
     tree_emit_kernel(const uint4* __restrict__ faces_in4,     // BUILD: input-order faces (16-byte records)
                      const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
                      uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
                      const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
-                     const LevelTable lv, uint32_t* done_counter)
+                     const __grid_constant__ LevelTable lv, uint32_t* done_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     __shared__ float2 s_top[3 * 16]; // heights 7..10 of the chunk: 8 + 4 + 2 + 1 nodes
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const uint32_t chunk = blockIdx.x;
+    EMIT_STAMP(0, tid == 0);
+    // block 0 is the finisher when the launch has one (the grid is then one CTA larger than the number of chunks). It is
+    // resident from the start and reduces groups as they complete; as the LAST block it would start in the last wave and
+    // then walk its groups one after the other: measured +13 us at T = 2^22.
+    const uint32_t has_finisher = gridDim.x * (uint32_t)kChunk >= T + (uint32_t)kChunk ? 1u : 0u;
+    if (has_finisher && blockIdx.x == 0)
+    {
+        emit_finisher(nodes, L, lv, done_counter, sm);
+        EMIT_STAMP(3, tid == 0);
+        return;
+    }
+    const uint32_t chunk = blockIdx.x - has_finisher;
     const uint32_t warp_leaf0 = chunk * kChunk + warp * kWarpLeaves;
     float2* wsm = sm + warp * (kWarpStageBytes / 8); // this warp's staging areas
 
@@ -713,8 +851,18 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
 #ifdef OIBVH_EXP_NOTOP
     return;
 #endif
+    if (has_finisher)
+    {
+        // warp 0 lane 0 stored the chunk root (height kChunkLevels) in the loop above: its release orders that store
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done_counter + (chunk >> 5)) : "memory");
+        EMIT_STAMP(1, tid == 32);
+        return;
+    }
     __syncthreads(); // every store of this CTA has been issued
+    EMIT_STAMP(1, tid == 32);
     if (warp != 0) return;
+    EMIT_STAMP(2, lane == 0);
+    EMIT_STAMP(3, lane == 0);
     uint32_t level = L - kChunkLevels, pos = chunk;
     uint32_t* ctr = done_counter;
     while (level > 0)
@@ -735,6 +883,7 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
             }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
+        EMIT_STAMP(3, lane == 0);
         if (!last) return;
         Box cur = Box{0, 0, 0, 0, 0, 0};
         if (lane < members) cur = load_box_cg(nodes, lv.off[level] + first + lane);
@@ -1143,7 +1292,9 @@ cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t*
                              const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s)
 {
     const uint32_t L = ceil_log2_u32(T);
-    const uint32_t chunks = (T + kChunk - 1) / kChunk;
+    uint32_t chunks = (T + kChunk - 1) / kChunk;
+    if (L > (uint32_t)kChunkLevels && chunks <= (uint32_t)OIBVH_EMIT_FINISHER_MAX_CHUNKS)
+        chunks += 1; // block 0 = the finisher CTA (levels above the chunk roots); the kernel sees the larger grid
     LevelTable lv;
     for (uint32_t l = 0; l < 32; l++)
     {
