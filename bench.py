@@ -364,7 +364,13 @@ def run_gpu_arm(args):
     from oibvh_b200 import distributed as obd
     gather = None
     if dist is not None:
-        cap = min(scene.pair_capacity(), 1 << 16)
+        # fixed-size exchange (no host round trip between frames): 4x this rank's warm-up pair count, rounded up to a
+        # power of two, at least 4096 records -- the all-gather moves world x cap x 16 bytes per frame
+        n_warm, _ = scene.counts()
+        cap = 4096
+        while cap < 4 * n_warm:
+            cap *= 2
+        cap = min(scene.pair_capacity(), cap)
         pairs_ptr, _ = scene.device_pairs()
         tdev = torch.device("cuda", dev)
         pairs_view = obd.pairs_tensor_from_device_ptr(pairs_ptr, cap, tdev)
@@ -540,6 +546,8 @@ def run_gpu_arm(args):
             "build_mtris_per_s": T / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None,
             "stage_ms": stage, "collide_phase_cycles": cyc, "pairs": n_pairs if dist is None else int(ctr_all[:, 1].sum().item()),
             "pairs_this_rank": n_pairs, "candidates": n_cand, "bvtt_rounds": rounds,
+            "gather": None if dist is None else {"records_per_rank": int(cap), "bytes_per_frame": int(world * cap * 16),
+                                                 "truncated": bool(int(ctr_all[:, 1].max().item()) > cap)},
             "gpu_launches": int(l1 - l0),
             "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,
             "clocks": clocks,
@@ -563,8 +571,15 @@ def run_gpu_arm(args):
                                "algorithmic_bytes_per_build": build_bytes, "ms_per_build": build_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
+            # the CPU baseline runs on the positions body B has NOW (after every rotation of the timed regions); the
+            # GPU count for exactly these positions is reported beside its pair count
             posB = tree_b.m_positions
+            ob.build_many([tree_a, tree_b])
+            scene.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
+            gpu_now = scene.counts()
             line["cpu_baseline"] = cpu_baseline_port(pos, faces, posB, mesh_a.m_aabb)
+            line["cpu_baseline"]["gpu_pairs_same_positions"] = int(gpu_now[0])
+            line["cpu_baseline"]["gpu_candidates_same_positions"] = int(gpu_now[1])
             # The unmodified reference GPU path only completes this scene up to ~10^5 triangles per body: it emits
             # BVTT children untested, so at 2 x 196 608 triangles its front outgrows its fixed 10 M-node buffers and
             # its unchecked level loop never terminates (measured on B200). Bounded sample: 2 x 98 304 triangles, with
