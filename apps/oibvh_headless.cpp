@@ -187,7 +187,7 @@ int manyBodies(const Options& o)
         m->translate(vec3(2.4f * (float)(i % side) + jx, 2.4f * (float)((i / side) % side) + jy, 2.4f * (float)(i / (side * side)) + jz));
         meshes.push_back(m);
         trees.push_back(std::make_shared<OibvhTree>(m)); // m_aabb = the translated construction-time box
-        mats.push_back(oibvh_math::translate(oibvh_math::identity(), vec3(0.04f * oibvh_mesh::hashNoise(i, 4, 99), 0.04f * oibvh_mesh::hashNoise(i, 5, 99), 0.0f)));
+        mats.push_back(oibvh_math::translate(oibvh_detail::mat4_identity(), vec3(0.04f * oibvh_mesh::hashNoise(i, 4, 99), 0.04f * oibvh_mesh::hashNoise(i, 5, 99), 0.0f)));
     }
     auto t0 = Clock::now();
     OibvhTree::buildMany(trees);

@@ -153,6 +153,15 @@ static_assert(sizeof(int_tri_pair_node_t) == sizeof(oibvh_int_tri_pair), "int_tr
 
 namespace oibvh_detail
 {
+// glm has no non-template identity(): glm::mat4(1.0f) there, the mini type's identity() otherwise
+inline oibvh_math::mat4 mat4_identity()
+{
+#ifdef OIBVH_FACADE_USE_GLM
+    return oibvh_math::mat4(1.0f);
+#else
+    return oibvh_math::identity();
+#endif
+}
 inline void check(int rc)
 {
     if (rc != OIBVH_OK) throw std::runtime_error(std::string("oibvh_b200: ") + oibvh_last_error());
@@ -214,13 +223,13 @@ public:
     // Mesh::rotate (mesh.cpp:171-178): about the mesh centre, angle in degrees
     void rotate(const oibvh_math::vec3 axis, const float angle)
     {
-        oibvh_math::mat4 m = oibvh_math::identity();
+        oibvh_math::mat4 m = oibvh_detail::mat4_identity();
         m = oibvh_math::translate(m, m_center);
         m = oibvh_math::rotate(m, oibvh_math::radians(angle), axis);
         m = oibvh_math::translate(m, -m_center);
         transform(m);
     }
-    void translate(const oibvh_math::vec3 t) { transform(oibvh_math::translate(oibvh_math::identity(), t)); }
+    void translate(const oibvh_math::vec3 t) { transform(oibvh_math::translate(oibvh_detail::mat4_identity(), t)); }
     // Mesh::transform (mesh.cpp:187-213). The reference round-trips every vertex through a GPU kernel; the values
     // are the same glm expression evaluated here on the host.
     void transform(const oibvh_math::mat4 M)

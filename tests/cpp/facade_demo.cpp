@@ -92,7 +92,7 @@ int main(int argc, char** argv)
                     // trees are created on the translated meshes (m_aabb is fixed at Mesh construction, as in the reference)
                     (copy ? single : many).push_back(std::make_shared<OibvhTree>(m));
                 }
-                mats.push_back(oibvh_math::translate(oibvh_math::identity(),
+                mats.push_back(oibvh_math::translate(oibvh_detail::mat4_identity(),
                                                      oibvh_math::vec3(0.05f * (float)(i % 5), -0.03f * (float)(i % 3), 0.0f)));
             }
             OibvhTree::buildMany(many);

@@ -38,3 +38,21 @@ def test_facade_header_mirrors_reference_surface():
                  "rotateZ", "translate", "transform", "m_aabbTree", "m_faces", "m_positions", "m_buildDone",
                  "m_vertices", "m_indices", "m_aabb", "m_verticesCount", "m_facesCount", "m_intTriPairs"]:
         assert name in text, name
+
+
+@pytest.mark.gpu
+def test_glm_mode_equals_mini_type_mode(ctx):
+    """the reference driver's lines built with glm as the facade's vector types (prebuilt in the build container
+    against the reference's vendored glm) and with the facade's own mini types print the same bits"""
+    mini, glm = (os.path.join(ROOT, "tests", "cpp", n) for n in ("glm_dropin_mini", "glm_dropin_glm"))
+    if not os.path.exists(mini):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    a = subprocess.run([mini], capture_output=True, text=True, timeout=120)
+    assert a.returncode == 0, a.stderr
+    fields = a.stdout.split()
+    assert fields[0] == "pairs" and int(fields[1]) > 0 and int(fields[11]) == 256, a.stdout  # icosphere(2): 320 faces, 321 internal nodes -> the first 256 boxes
+    if not os.path.exists(glm):
+        pytest.skip("tests/cpp/glm_dropin_glm not prebuilt (needs the reference's glm)")
+    b = subprocess.run([glm], capture_output=True, text=True, timeout=120)
+    assert b.returncode == 0, b.stderr
+    assert a.stdout == b.stdout
