@@ -58,6 +58,8 @@ def make_meshes(nu=NU, nv=NV, shuffle=True):
 # clocks sampler (nvidia-smi) -- runs during the timed region
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region. NVML in a thread every ~2 ms (the timed region
+    of the default run is ~14 ms, shorter than one nvidia-smi period); falls back to `nvidia-smi -lms 100`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -65,9 +67,34 @@ class ClockSampler:
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []       # nvidia-smi fallback: (time, csv line)
+        self.samples = []     # NVML: (time, sm MHz, reasons bitmask)
+        self.sm_max = None
+        self.nvml = None
+        self.stop_flag = False
+        self.thread = None
+
+    def _nvml_index(self):
+        # CUDA_VISIBLE_DEVICES remaps CUDA ordinals; NVML enumerates physical devices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and all(v.strip().isdigit() for v in ids) and self.gpu < len(ids):
+            return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # fails here rather than in the thread
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -77,11 +104,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _pump_nvml(self):
+        pynvml, h = self.nvml
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                clk = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                self.samples.append((time.time(), clk, int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            time.sleep(0.01)
+            self.stop_flag = True
+            pynvml = self.nvml[0]
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            inside = [(c, r) for ts, c, r in self.samples if t0 <= ts <= t1] or [(c, r) for _, c, r in self.samples]
+            reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in inside))
+            return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.sm_max,
+                    "reasons": reasons, "samples": len(inside), "source": "NVML, ~2 ms period, inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +161,7 @@ class ClockSampler:
                 except (ValueError, IndexError):
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -604,8 +655,8 @@ CTR_BYTES = 64 * 4
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
