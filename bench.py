@@ -423,16 +423,19 @@ def run_gpu_arm(args):
             cap *= 2
         cap = min(scene.pair_capacity(), cap)
         pairs_ptr, _ = scene.device_pairs()
+        ctr_ptr = scene.device_counters()
         tdev = torch.device("cuda", dev)
-        pairs_view = obd.pairs_tensor_from_device_ptr(pairs_ptr, cap, tdev)
-        ctr_view = obd.pairs_tensor_from_device_ptr(scene.device_counters(), 1, tdev)  # 4 words: cand, pairs, ovf, -
-        pairs_all = torch.empty((world * cap, 4), dtype=torch.int32, device=tdev)
-        ctr_all = torch.empty((world, 4), dtype=torch.int32, device=tdev)
+        HEAD = 32  # the 512-byte counter block is the head of the pair-list allocation (include/oibvh_b200.h)
+        assert pairs_ptr == ctr_ptr + HEAD * 16, "counter block does not precede the pair list"
+        # ONE all-gather per frame: [counter block | first `cap` pair records] of every rank
+        block_view = obd.pairs_tensor_from_device_ptr(ctr_ptr, HEAD + cap, tdev)
+        block_all = torch.empty((world * (HEAD + cap), 4), dtype=torch.int32, device=tdev)
+        ctr_all = block_all.view(world, HEAD + cap, 4)[:, 0, :]        # row 0 of a block: cand, pairs, overflow, -
+        pairs_all = block_all.view(world, HEAD + cap, 4)[:, HEAD:, :]  # rank r's pairs: pairs_all[r, :count_r]
 
         def gather():
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(ctr_all, ctr_view)
-                dist.all_gather_into_tensor(pairs_all, pairs_view)
+                dist.all_gather_into_tensor(block_all, block_view)
         gather()
         torch.cuda.synchronize()
 
@@ -501,6 +504,8 @@ def run_gpu_arm(args):
         mb.transform(M_rot)
         rot_frames.append(torch.from_numpy(mb.m_positions.copy()).pin_memory())
     pair_host = torch.empty((max(4 * n_pairs, 1 << 16), 4), dtype=torch.int32).pin_memory()
+    if dist is not None:
+        gathered_host = torch.empty((world * (HEAD + cap), 4), dtype=torch.int32).pin_memory()
 
     def e2e_upload(i):
         tree_a.set_positions_from_host_ptr(host_a.data_ptr())
@@ -521,19 +526,22 @@ def run_gpu_arm(args):
         if dist is None:
             # one C-ABI call: waits for the frame, reads the counters, copies the pair list into the pinned buffer
             return scene.get_pairs_into(pair_host.data_ptr())
-        n, _ = scene.counts()  # D2H of the counters (sync)
-        ptr, n = scene.device_pairs()
-        local = obd.pairs_tensor_from_device_ptr(ptr, n, torch.device("cuda", dev))
-        if dist is not None:
+        # N > 1: the fixed-size exchange of the timed region (counter blocks + padded pair lists, two all-gathers on
+        # the frame's stream, no host round trip in between), then ONE device->host read of everything
+        gather()
+        with torch.cuda.stream(stream):
+            gathered_host.copy_(block_all, non_blocking=True)
+        stream.synchronize()
+        counts_now = gathered_host.view(world, HEAD + cap, 4)[:, 0, 1].tolist()
+        if max(counts_now) > cap:  # a shard outgrew the fixed exchange: exact (slower) variable-size gather
+            ptr, n = scene.device_pairs()
+            local = obd.pairs_tensor_from_device_ptr(ptr, n, torch.device("cuda", dev))
             with torch.cuda.stream(stream):
                 full = obd.gather_pairs(local, n)
-            n = full.shape[0]
-            local = full
-        if n:
-            with torch.cuda.stream(stream):
-                pair_host[:n].copy_(local[:n], non_blocking=True)
-        stream.synchronize()
-        return n
+                pair_host[:full.shape[0]].copy_(full, non_blocking=True)
+            stream.synchronize()
+            return int(full.shape[0])
+        return int(sum(counts_now))  # rank r's pairs: gathered_host.view(world, HEAD + cap, 4)[r, HEAD:HEAD + counts_now[r]]
 
     for i in range(2):
         e2e_frame(i)
@@ -549,7 +557,7 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     h2d = 2 * 12 * V
-    d2h = CTR_BYTES + 16 * (tot_pairs // max(n_e2e, 1))
+    d2h = CTR_BYTES + 16 * (tot_pairs // max(n_e2e, 1)) if dist is None else 16 * world * (HEAD + cap)
     # the same loop with the NEXT step's host->device copies enqueued before this step's result is awaited (every
     # step still uploads its own inputs and reads its own result; reported beside e2e, not instead of it)
     e2e_upload(0)
@@ -597,7 +605,8 @@ def run_gpu_arm(args):
             "build_mtris_per_s": T / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None,
             "stage_ms": stage, "collide_phase_cycles": cyc, "pairs": n_pairs if dist is None else int(ctr_all[:, 1].sum().item()),
             "pairs_this_rank": n_pairs, "candidates": n_cand, "bvtt_rounds": rounds,
-            "gather": None if dist is None else {"records_per_rank": int(cap), "bytes_per_frame": int(world * cap * 16),
+            "gather": None if dist is None else {"records_per_rank": int(cap), "collectives_per_frame": 1,
+                                                 "bytes_per_frame": int(world * (HEAD + cap) * 16),
                                                  "truncated": bool(int(ctr_all[:, 1].max().item()) > cap)},
             "gpu_launches": int(l1 - l0),
             "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,

@@ -179,7 +179,11 @@ int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_
  * Returns the number of phases written. Replaces the reference's per-launch stopwatch (scene.cu:299-302, 419). */
 int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases, uint32_t* n_phases);
 /* device view of the counter block of the last detection: word 0 = candidates, word 1 = pairs (lets a caller chain
- * a collective on the stream without a host round trip). Does not synchronise. */
+ * a collective on the stream without a host round trip). Does not synchronise. After the first detection the block
+ * (512 bytes = 32 records) is the head of the pair-list allocation: the pair list returned by
+ * oibvh_scene_device_pairs starts exactly 512 bytes behind it, so ONE collective over
+ * [counters, counters + 512 + n * 16) moves the counts and the first n pair records together. Both pointers change
+ * when the queues are re-allocated after an overflow (query them again after oibvh_scene_get_counts). */
 int oibvh_scene_device_counters(oibvh_scene* scene, const uint32_t** dev_counters);
 /* current capacity (records) of the device pair list returned by oibvh_scene_device_pairs */
 int oibvh_scene_pair_capacity(oibvh_scene* scene, uint32_t* capacity);

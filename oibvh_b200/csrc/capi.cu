@@ -133,7 +133,13 @@ struct oibvh_scene
     uint4* cand = nullptr;
     uint4* pairs = nullptr;
     uint32_t front_cap = 0, cand_cap = 0, pair_cap = 0;
-    uint32_t* counters = nullptr;   // device, CTR_WORDS
+    // Device counter block (CTR_WORDS). Once the work queues exist it is the HEAD of the pair-list allocation:
+    // [counters: CTR_WORDS x 4 bytes = 32 records][pairs: pair_cap records], so a multi-GPU caller moves the counts
+    // and the pair list with ONE collective (oibvh_scene_device_counters). counters_own is the stand-alone block a
+    // scene starts with (and falls back to while the queues are being re-allocated).
+    uint32_t* counters = nullptr;
+    uint32_t* counters_own = nullptr;
+    uint4* pair_block = nullptr;
     uint32_t* h_counters = nullptr; // pinned host mirror
     uint32_t rank = 0, world = 1;
     uint32_t last_entry = 0, last_expand = 0, last_rounds = 0; // parameters of the last enqueued detection
@@ -298,8 +304,9 @@ void scene_free_buffers(oibvh_scene* s)
     cudaFree(s->front[0]);
     cudaFree(s->front[1]);
     cudaFree(s->cand);
-    cudaFree(s->pairs);
-    s->front[0] = s->front[1] = s->cand = s->pairs = nullptr;
+    cudaFree(s->pair_block);
+    s->front[0] = s->front[1] = s->cand = s->pairs = s->pair_block = nullptr;
+    s->counters = s->counters_own;
 }
 
 int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, uint32_t pair_cap)
@@ -307,9 +314,17 @@ int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, u
     scene_free_buffers(s);
     s->ctx->generation++;
     int rc;
+    static_assert(CTR_WORDS * sizeof(uint32_t) % sizeof(uint4) == 0, "the counter block is a whole number of records");
+    constexpr size_t kCtrRecords = CTR_WORDS * sizeof(uint32_t) / sizeof(uint4);
     if ((rc = dev_alloc(&s->front[0], front_cap)) || (rc = dev_alloc(&s->front[1], front_cap)) ||
-        (rc = dev_alloc(&s->cand, cand_cap)) || (rc = dev_alloc(&s->pairs, pair_cap)))
+        (rc = dev_alloc(&s->cand, cand_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)))
         return rc;
+    s->counters = reinterpret_cast<uint32_t*>(s->pair_block);
+    s->pairs = s->pair_block + kCtrRecords;
+    {
+        cudaError_t e = cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, s->ctx->stream);
+        if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+    }
     s->front_cap = front_cap;
     s->cand_cap = cand_cap;
     s->pair_cap = pair_cap;
@@ -1189,16 +1204,17 @@ extern "C" int oibvh_scene_create(oibvh_ctx* ctx, oibvh_scene** out)
     oibvh_scene* s = new (std::nothrow) oibvh_scene;
     if (!s) return fail(OIBVH_ERR_NOMEM, "host allocation failed");
     s->ctx = ctx;
-    int rc = dev_alloc(&s->counters, (size_t)CTR_WORDS);
+    int rc = dev_alloc(&s->counters_own, (size_t)CTR_WORDS);
     if (rc)
     {
         delete s;
         return rc;
     }
+    s->counters = s->counters_own;
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&s->h_counters), sizeof(uint32_t) * CTR_WORDS);
     if (e != cudaSuccess)
     {
-        cudaFree(s->counters);
+        cudaFree(s->counters_own);
         delete s;
         return fail(OIBVH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
     }
@@ -1214,7 +1230,7 @@ extern "C" int oibvh_scene_destroy(oibvh_scene* scene)
     cudaStreamSynchronize(scene->ctx->stream);
     scene_free_buffers(scene);
     cudaFree(scene->d_objs);
-    cudaFree(scene->counters);
+    cudaFree(scene->counters_own);
     cudaFreeHost(scene->h_counters);
     delete scene;
     return OIBVH_OK;
