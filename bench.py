@@ -425,17 +425,17 @@ def run_gpu_arm(args):
         pairs_ptr, _ = scene.device_pairs()
         ctr_ptr = scene.device_counters()
         tdev = torch.device("cuda", dev)
-        HEAD = 32  # the 512-byte counter block is the head of the pair-list allocation (include/oibvh_b200.h)
+        HEAD = obd.HEAD_RECORDS  # the 512-byte counter block is the head of the pair-list allocation
         assert pairs_ptr == ctr_ptr + HEAD * 16, "counter block does not precede the pair list"
         # ONE all-gather per frame: [counter block | first `cap` pair records] of every rank
-        block_view = obd.pairs_tensor_from_device_ptr(ctr_ptr, HEAD + cap, tdev)
+        block_view = obd.block_view(ctr_ptr, cap, tdev)
         block_all = torch.empty((world * (HEAD + cap), 4), dtype=torch.int32, device=tdev)
         ctr_all = block_all.view(world, HEAD + cap, 4)[:, 0, :]        # row 0 of a block: cand, pairs, overflow, -
         pairs_all = block_all.view(world, HEAD + cap, 4)[:, HEAD:, :]  # rank r's pairs: pairs_all[r, :count_r]
 
         def gather():
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(block_all, block_view)
+                obd.gather_blocks(block_all, block_view)
         gather()
         torch.cuda.synchronize()
 
@@ -532,8 +532,8 @@ def run_gpu_arm(args):
         with torch.cuda.stream(stream):
             gathered_host.copy_(block_all, non_blocking=True)
         stream.synchronize()
-        counts_now = gathered_host.view(world, HEAD + cap, 4)[:, 0, 1].tolist()
-        if max(counts_now) > cap:  # a shard outgrew the fixed exchange: exact (slower) variable-size gather
+        counts_now, _, truncated = obd.unpack_blocks(gathered_host, world, cap)
+        if truncated:  # a shard outgrew the fixed exchange: exact (slower) variable-size gather
             ptr, n = scene.device_pairs()
             local = obd.pairs_tensor_from_device_ptr(ptr, n, torch.device("cuda", dev))
             with torch.cuda.stream(stream):

@@ -39,3 +39,27 @@ def pairs_tensor_from_device_ptr(ptr, n, device):
     h.__cuda_array_interface__ = {"shape": (int(n), 4), "typestr": "<i4", "data": (int(ptr), False), "version": 3,
                                   "strides": None}
     return torch.as_tensor(h, device=device)
+
+
+# ---- fixed-size exchange: ONE collective per frame -----------------------------------------------------------------
+# A scene's 512-byte counter block is the head of its pair-list allocation (include/oibvh_b200.h,
+# oibvh_scene_device_counters), so [counter block | first `cap` pair records] is one contiguous device range.
+HEAD_RECORDS = 32  # 512 bytes / 16-byte records; row 0 = (candidates, pairs, overflow flags, barrier word)
+
+
+def block_view(counters_ptr, cap, device):
+    """zero-copy int32 [HEAD_RECORDS + cap, 4] view of a scene's [counter block | pair list] device range"""
+    return pairs_tensor_from_device_ptr(counters_ptr, HEAD_RECORDS + int(cap), device)
+
+
+def gather_blocks(out, block, group=None):
+    """all-gather every rank's block into out ([world * (HEAD_RECORDS + cap), 4]); enqueue-only on NCCL"""
+    dist.all_gather_into_tensor(out, block, group=group)
+
+
+def unpack_blocks(gathered, world, cap):
+    """-> (per-rank pair counts, list of per-rank [min(count, cap), 4] views, truncated?) from a gathered buffer"""
+    v = gathered.view(world, HEAD_RECORDS + int(cap), 4)
+    counts = [int(c) for c in v[:, 0, 1].tolist()]
+    parts = [v[r, HEAD_RECORDS:HEAD_RECORDS + min(counts[r], int(cap))] for r in range(world)]
+    return counts, parts, max(counts) > int(cap)

@@ -98,3 +98,45 @@ def test_gather_pairs_world2_gloo():
     want = np.concatenate([np.arange(8).reshape(2, 4), np.arange(12).reshape(3, 4) + 1000]).astype(np.int32)
     for r in range(2):
         assert np.array_equal(out[r], want)
+
+
+def _block_worker(rank, world, port_no, q):
+    import torch
+    import torch.distributed as dist
+    from oibvh_b200 import distributed as obd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cap = 8
+        # what a scene's device range looks like: 32-record counter block (row 0 = cand, pairs, flags, -) + pair list
+        n = [3, 11][rank]  # rank 1 overflows the fixed exchange
+        block = torch.full((obd.HEAD_RECORDS + cap, 4), -7, dtype=torch.int32)
+        block[0] = torch.tensor([5 * n, n, 0, 0], dtype=torch.int32)
+        m = min(n, cap)
+        block[obd.HEAD_RECORDS:obd.HEAD_RECORDS + m] = torch.arange(m * 4, dtype=torch.int32).reshape(m, 4) + 1000 * rank
+        out = torch.empty((world * (obd.HEAD_RECORDS + cap), 4), dtype=torch.int32)
+        obd.gather_blocks(out, block)
+        counts, parts, truncated = obd.unpack_blocks(out, world, cap)
+        q.put((rank, counts, [p.numpy().copy() for p in parts], truncated))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_single_collective_block_exchange_world2_gloo():
+    """[counter block | pair list] of every rank in ONE all-gather (the multi-GPU frame's only exchange)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_block_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, counts, parts, truncated in res:
+        assert counts == [3, 11] and truncated  # rank 1 holds 11 > cap = 8 records: reported, never silently dropped
+        assert np.array_equal(parts[0], np.arange(12).reshape(3, 4))
+        assert np.array_equal(parts[1], np.arange(32).reshape(8, 4) + 1000)
