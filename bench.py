@@ -417,11 +417,9 @@ def run_gpu_arm(args):
     if dist is not None:
         # fixed-size exchange (no host round trip between frames): 4x this rank's warm-up pair count, rounded up to a
         # power of two, at least 4096 records -- the all-gather moves world x cap x 16 bytes per frame
+        # (agreed across ranks by all-reduce: per-rank counts differ, and a collective whose size differs per rank hangs)
         n_warm, _ = scene.counts()
-        cap = 4096
-        while cap < 4 * n_warm:
-            cap *= 2
-        cap = min(scene.pair_capacity(), cap)
+        cap = obd.agree_capacity(n_warm, floor=4096, ceiling=scene.pair_capacity(), device=torch.device("cuda", dev))
         pairs_ptr, _ = scene.device_pairs()
         ctr_ptr = scene.device_counters()
         tdev = torch.device("cuda", dev)

@@ -63,3 +63,16 @@ def unpack_blocks(gathered, world, cap):
     counts = [int(c) for c in v[:, 0, 1].tolist()]
     parts = [v[r, HEAD_RECORDS:HEAD_RECORDS + min(counts[r], int(cap))] for r in range(world)]
     return counts, parts, max(counts) > int(cap)
+
+
+def agree_capacity(n_local, floor=4096, ceiling=None, device=None, group=None):
+    """Fixed per-rank record count of the block exchange, IDENTICAL on every rank (a collective with different sizes
+    per rank never completes): 4x the LARGEST per-rank pair count (all-reduce MAX), rounded up to a power of two,
+    at least `floor`, at most `ceiling` (the smallest pair-list capacity, also agreed by all-reduce MIN)."""
+    t = torch.tensor([int(n_local), -int(ceiling) if ceiling is not None else -(1 << 62)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    n_max, ceil_min = int(t[0].item()), -int(t[1].item())
+    cap = int(floor)
+    while cap < 4 * n_max:
+        cap *= 2
+    return min(cap, ceil_min)

@@ -140,3 +140,44 @@ def test_single_collective_block_exchange_world2_gloo():
         assert counts == [3, 11] and truncated  # rank 1 holds 11 > cap = 8 records: reported, never silently dropped
         assert np.array_equal(parts[0], np.arange(12).reshape(3, 4))
         assert np.array_equal(parts[1], np.arange(32).reshape(8, 4) + 1000)
+
+
+def _cap_worker(rank, world, port_no, q):
+    import torch
+    import torch.distributed as dist
+    from oibvh_b200 import distributed as obd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_local = [700, 1100, 90][rank]          # 4x -> 2800 / 4400 / 360: a rank-local rule would give 4096 / 8192 / 4096
+        ceiling = [1 << 19, 1 << 19, 1 << 20][rank]
+        cap = obd.agree_capacity(n_local, floor=4096, ceiling=ceiling)
+        cap_small = obd.agree_capacity(n_local, floor=4096, ceiling=[6000, 5000, 7000][rank])
+        # the exchange itself with the agreed size, world = 3
+        block = torch.full((obd.HEAD_RECORDS + cap, 4), rank, dtype=torch.int32)
+        block[0] = torch.tensor([0, n_local, 0, 0], dtype=torch.int32)
+        out = torch.empty((world * (obd.HEAD_RECORDS + cap), 4), dtype=torch.int32)
+        obd.gather_blocks(out, block)
+        counts, parts, truncated = obd.unpack_blocks(out, world, cap)
+        q.put((rank, cap, cap_small, counts, [int(p[0, 0]) for p in parts], truncated))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_capacity_is_agreed_across_ranks_world3_gloo():
+    """regression: the fixed exchange size must not depend on the rank's own pair count (it hung at 4 GPUs)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_cap_worker, args=(r, 3, port_no, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(3)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, cap, cap_small, counts, firsts, truncated in res:
+        assert cap == 8192 and cap_small == 5000          # MAX of the counts, MIN of the ceilings: same on every rank
+        assert counts == [700, 1100, 90] and firsts == [0, 1, 2] and not truncated
