@@ -667,6 +667,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # a wedged collective or GPU must not hold the driver for ever: fail the process loudly after ten minutes
+    def _watchdog():
+        sys.stderr.write("bench.py: no result after 600 s -- aborting (rank %s)\n" % os.environ.get("RANK", "0"))
+        sys.stderr.flush()
+        os._exit(3)
+    wd = threading.Timer(600.0, _watchdog)
+    wd.daemon = True
+    wd.start()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
