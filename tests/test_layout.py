@@ -73,3 +73,31 @@ def test_port_layout_equals_unmodified_reference(port, ref, T):
         lev = (i + 1).bit_length() - 1
         if lev < L:
             assert port.have_rchild(i, L, vl) == bool(ref.lib.ref_oibvh_have_rchild(i, L, vl))
+
+
+def test_layout_properties_random_sizes(port):
+    """hypothesis: for random T up to 2^26 (the node-position field of a BVTT record) and random (level, position),
+    the device's closed-form addressing equals the restated reference mapping, both directions"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(min_value=2, max_value=1 << 26), st.data())
+    def check(T, data):
+        L = ceil_log2(T)
+        vl = (1 << L) - T
+        N = port.get_size(T)
+        assert N == 2 * T - 1 + bin(vl).count("1") == level_offset(T, L, L) + T
+        l = data.draw(st.integers(min_value=0, max_value=L))
+        cnt = level_count(T, L, l)
+        assert cnt == port.level_real_count(l, L, vl)
+        p = data.draw(st.integers(min_value=0, max_value=cnt - 1))
+        implicit = (1 << l) - 1 + p
+        real = level_offset(T, L, l) + p
+        assert port.implicit_to_real(implicit, L, vl) == real
+        assert port.real_to_implicit(real, L, vl) == implicit
+        if l < L:
+            assert port.have_rchild(implicit, L, vl) == (2 * p + 1 < level_count(T, L, l + 1))
+            # the children of (l, p) are (l+1, 2p) and, when kept, (l+1, 2p+1): parents are never virtual
+            assert 2 * p < level_count(T, L, l + 1)
+
+    check()
