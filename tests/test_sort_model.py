@@ -1,0 +1,42 @@
+"""The planned MSD equal-count sort (tools/sort_model.py) as an executable model: same permutation as
+a stable sort by key -- i.e. as thrust::stable_sort_by_key (src/cuda/oibvhTree.cu:295-296) -- or an explicit fallback."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import sort_model  # noqa: E402
+from oibvh_b200 import meshgen  # noqa: E402
+
+
+def test_model_equals_stable_sort_on_mesh_keys(port):
+    for pos, faces in (meshgen.blob(256, 192, seed=1234), meshgen.icosphere(5)):
+        faces = meshgen.shuffle_faces(faces)
+        keys = port.morton_keys(pos, faces, port.mesh_aabb(pos))
+        perm = sort_model.msd_equal_count_sort(keys, n_chunks=37, window=1024, capacity=4096)
+        assert perm is not None
+        assert np.array_equal(perm, np.argsort(keys, kind="stable"))
+        assert np.array_equal(perm, port.stable_sort_perm(keys))
+
+
+def test_model_ties_small_inputs_and_fallback():
+    rng = np.random.default_rng(3)
+    # heavy ties: few distinct keys, must stay in input order inside a key
+    keys = (rng.integers(0, 50, 20000).astype(np.uint32) << 14) | rng.integers(0, 3, 20000).astype(np.uint32)
+    perm = sort_model.msd_equal_count_sort(keys, n_chunks=8, fine_bits=16, window=512, capacity=2048)
+    assert perm is not None and np.array_equal(perm, np.argsort(keys, kind="stable"))
+    for n in (1, 2, 3, 31, 1000):
+        k = rng.integers(0, 1 << 30, n).astype(np.uint32)
+        assert np.array_equal(sort_model.msd_equal_count_sort(k, n_chunks=5), np.argsort(k, kind="stable"))
+    # a heavy fine bin (> capacity - window) is a range of its own; above the capacity the model asks for the fallback
+    heavy = np.concatenate([rng.integers(0, 1 << 30, 3000).astype(np.uint32), np.full(3500, 123 << 14, np.uint32),
+                            rng.integers(0, 1 << 30, 3000).astype(np.uint32)])
+    rng.shuffle(heavy)
+    perm = sort_model.msd_equal_count_sort(heavy, n_chunks=7, window=1024, capacity=4096)
+    assert perm is not None and np.array_equal(perm, np.argsort(heavy, kind="stable"))
+    plan = sort_model.plan_ranges(heavy, 16, 1024, 4096)
+    sizes = np.bincount(plan[3][plan[0]])
+    assert sizes.max() <= 4096 and 3500 in sizes
+    assert sort_model.msd_equal_count_sort(np.full(5000, 123 << 14, np.uint32), window=1024, capacity=4096) is None
