@@ -113,6 +113,7 @@ struct oibvh_tree
     uint32_t* sort_ctl = nullptr; // [hist: passes*radix][ticket: passes (padded to 64)][status: passes*tiles*radix]
     size_t sort_ctl_words = 0;
     uint32_t* done_counter = nullptr;
+    uint32_t* msd_ctl = nullptr; // EXPERIMENTAL sort (OIBVH_SORT_MSD=1): allocated on first use
     // T <= kSmallTreeMax: built / refitted by one CTA (small_tree_kernel); no second sort buffers, no control blocks
     bool small = false;
     SmallTreeDesc* d_small = nullptr; // this tree's entry for single-tree launches
@@ -212,6 +213,7 @@ void tree_free(oibvh_tree* t)
     cudaFree(t->vals_b);
     cudaFree(t->d_small);
     cudaFree(t->sort_ctl);
+    cudaFree(t->msd_ctl);
     cudaFree(t->done_counter);
     if (t->ev_uploaded) cudaEventDestroy(t->ev_uploaded);
     if (t->ev_consumed) cudaEventDestroy(t->ev_consumed);
@@ -733,6 +735,41 @@ extern "C" int oibvh_tree_transform(oibvh_tree* tree, const float M[16])
     return OIBVH_OK;
 }
 
+static bool msd_sort_requested()
+{
+    const char* e = getenv("OIBVH_SORT_MSD");
+    return e != nullptr && e[0] == '1';
+}
+
+// EXPERIMENTAL path of oibvh_tree_build: keys are in tree->keys_a. *sorted = true when (keys_a, vals_a) hold the result.
+static int msd_sort_try(oibvh_tree* tree, bool* sorted)
+{
+    *sorted = false;
+    oibvh_ctx* ctx = tree->ctx;
+    static bool configured = false;
+    if (!configured)
+    {
+        CU(msd_sort_configure());
+        configured = true;
+    }
+    if (tree->T > msd_sort_capacity()) return OIBVH_OK;
+    if (!tree->msd_ctl)
+    {
+        int rc = dev_alloc(&tree->msd_ctl, msd_sort_ctl_words());
+        if (rc) return rc;
+    }
+    CU(launch_msd_plan(tree->keys_a, tree->T, tree->msd_ctl, ctx->stream));
+    count_launch(ctx, 2);
+    uint32_t head[4] = {0, 0, 0, 1};
+    CU(cudaMemcpyAsync(head, tree->msd_ctl, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (head[3] != 0 || head[2] == 0) return OIBVH_OK; // a bin above the range capacity / too many ranges: 4-pass sort
+    CU(launch_msd_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->msd_ctl, ctx->stream));
+    count_launch(ctx);
+    *sorted = true;
+    return OIBVH_OK;
+}
+
 extern "C" int oibvh_tree_build(oibvh_tree* tree)
 {
     REQUIRE(tree != nullptr, "tree is NULL");
@@ -762,8 +799,19 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
         CU(cudaMemsetAsync(tree->sort_ctl, 0, 64 * sizeof(uint32_t), s));
         CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
         count_launch(ctx);
-        CU(launch_coop_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->sort_ctl, s));
-        count_launch(ctx);
+        bool sorted = false;
+        if (msd_sort_requested() && !ctx->capturing)
+        {
+            // EXPERIMENTAL, opt-in (OIBVH_SORT_MSD=1): equal-count MSD partition + range-local sorts (sort_msd.cu).
+            // The plan is read back (one host sync) to decide between it and the 4-pass sort; not capturable.
+            int rc = msd_sort_try(tree, &sorted);
+            if (rc) return rc;
+        }
+        if (!sorted)
+        {
+            CU(launch_coop_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->sort_ctl, s));
+            count_launch(ctx);
+        }
     }
     else
     {

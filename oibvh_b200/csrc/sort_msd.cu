@@ -1,0 +1,545 @@
+// EXPERIMENTAL -- off by default (OIBVH_SORT_MSD=1 selects it in oibvh_tree_build for single-wave sizes outside a
+// graph capture). Written against the executable model tools/sort_model.py; it has been compiled for
+// sm_100a but NOT yet run on a GPU: the shipped path is the cooperative 4-pass LSD sort in sort_coop.cu.
+//
+// Stable sort of (30-bit Morton key, face id) with ONE global data movement instead of four:
+//   1. msd_fine_hist_kernel   histogram of the top 16 key bits (65 536 bins)
+//   2. msd_plan_kernel        bins -> ranges of at most kMsdCap keys that are contiguous in the output: a bin opens a
+//                             range when it starts in another kMsdWindow-key output window than the non-empty bin
+//                             before it, or when it or that bin is heavy (> kMsdCap - kMsdWindow keys); writes the
+//                             bin -> range table, the range starts, and a fallback flag (a bin above kMsdCap keys, or
+//                             more than kMsdMaxRanges ranges) that sends the caller to the 4-pass sort
+//   3. msd_sort_kernel        cooperative: stable partition of the input by range id (per-CTA ranking, counts matrix,
+//                             row scan between two grid barriers, as in sort_coop.cu but the "digit" is the range id),
+//                             then every range is sorted stably by its full key inside one CTA's shared memory
+//                             (four 8-bit passes over 16-bit local indices, the keys stay put) and written in place.
+// Stability: the partition keeps input order inside a range (chunks ordered by CTA, keys inside a chunk ranked in
+// (warp, item, lane) order), the range-local LSD passes are stable, and ranges are ordered by key: the result is the
+// stable order of thrust::stable_sort_by_key (src/cuda/oibvhTree.cu:295-296).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace oibvh
+{
+
+constexpr int kMsdThreads = 512;
+constexpr int kMsdWarps = kMsdThreads / 32;
+constexpr int kMsdIpt = 16;
+constexpr int kMsdCap = kMsdThreads * kMsdIpt; // 8192 keys: one CTA's chunk of the partition, and the largest range
+constexpr int kMsdWindow = 4096;
+constexpr int kMsdFineBits = 16;
+constexpr int kMsdFineBins = 1 << kMsdFineBits;
+constexpr int kMsdFineShift = 30 - kMsdFineBits;
+constexpr int kMsdMaxRanges = 1024;
+constexpr int kMsdRangeBits = 10;
+constexpr int kMsdRowSeg = 10;      // row scan: entries per lane -> grids up to 320 CTAs
+constexpr int kMsdPlanThreads = 1024;
+constexpr int kMsdValBits = 21;     // input positions are packed with the range id in one word: T < 2^21
+
+// control block (uint32 words)
+constexpr size_t kMsdCtlBarrier = 0, kMsdCtlFail = 1, kMsdCtlRanges = 2, kMsdCtlFallback = 3;
+constexpr size_t kMsdCtlRangeStart = 64;                                       // kMsdMaxRanges + 1 words
+constexpr size_t kMsdCtlRangeOfBin = kMsdCtlRangeStart + kMsdMaxRanges + 64;   // 65 536 x uint16
+constexpr size_t kMsdCtlHist = kMsdCtlRangeOfBin + kMsdFineBins / 2;           // 65 536 words
+constexpr size_t kMsdCtlMat = kMsdCtlHist + kMsdFineBins;                      // kMsdMaxRanges x grid words
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. fine histogram
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msd_fine_hist_kernel(const uint32_t* __restrict__ keys, uint32_t T,
+                                                            uint32_t* __restrict__ hist)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x)
+        atomicAdd(hist + (__ldg(keys + i) >> kMsdFineShift), 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block-wide exclusive scan (THREADS a multiple of 32, <= 1024); s_warp holds >= 33 words; returns the exclusive
+// prefix of v over the thread index and the block total
+// ---------------------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ uint32_t msd_block_scan(uint32_t v, uint32_t* s_warp, uint32_t* total)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const uint32_t w = lane < (uint32_t)(THREADS / 32) ? s_warp[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += n;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const uint32_t r = inc - v + s_warp[warp];
+    *total = s_warp[32];
+    __syncthreads(); // s_warp may be reused by the caller
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. plan: one CTA, thread t owns the 64 consecutive bins [64 t, 64 t + 64)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(uint32_t* __restrict__ ctl, uint32_t T)
+{
+    constexpr int PER = kMsdFineBins / kMsdPlanThreads; // 64
+    __shared__ uint32_t s_warp[40];
+    __shared__ uint32_t s_last_start[kMsdPlanThreads]; // start of the thread's last non-empty bin
+    __shared__ uint32_t s_last_count[kMsdPlanThreads]; // its count (0: the thread has no non-empty bin)
+    const uint32_t tid = threadIdx.x;
+    const uint32_t* hist = ctl + kMsdCtlHist;
+    uint16_t* range_of_bin = reinterpret_cast<uint16_t*>(ctl + kMsdCtlRangeOfBin);
+    uint32_t* range_start = ctl + kMsdCtlRangeStart;
+    const uint32_t b0 = tid * PER;
+
+    // ---- bin starts: exclusive prefix of the histogram ----
+    uint32_t sum = 0, mx = 0;
+#pragma unroll 8
+    for (int k = 0; k < PER; k++)
+    {
+        const uint32_t c = __ldcg(hist + b0 + k);
+        sum += c;
+        mx = max(mx, c);
+    }
+    uint32_t total = 0;
+    const uint32_t seg_start = msd_block_scan<kMsdPlanThreads>(sum, s_warp, &total);
+    const uint32_t block_max = __reduce_max_sync(0xffffffffu, mx);
+    if ((tid & 31u) == 0) s_warp[tid >> 5] = block_max;
+    __syncthreads();
+    uint32_t max_bin = 0;
+    for (int w = 0; w < kMsdPlanThreads / 32; w++) max_bin = max(max_bin, s_warp[w]);
+    __syncthreads();
+
+    // ---- the thread's last non-empty bin (carried to the threads behind it) ----
+    {
+        uint32_t run = seg_start, ls = 0, lc = 0;
+#pragma unroll 8
+        for (int k = 0; k < PER; k++)
+        {
+            const uint32_t c = __ldcg(hist + b0 + k);
+            if (c)
+            {
+                ls = run;
+                lc = c;
+            }
+            run += c;
+        }
+        s_last_start[tid] = ls;
+        s_last_count[tid] = lc;
+    }
+    __syncthreads();
+    // nearest non-empty bin before this thread's segment
+    bool have_prev = false, prev_heavy = false;
+    uint32_t prev_win = 0;
+    for (int t = (int)tid - 1; t >= 0; t--)
+        if (s_last_count[t])
+        {
+            have_prev = true;
+            prev_heavy = s_last_count[t] > (uint32_t)(kMsdCap - kMsdWindow);
+            prev_win = s_last_start[t] / kMsdWindow;
+            break;
+        }
+
+    // ---- how many ranges open inside this segment ----
+    uint32_t opens = 0;
+    {
+        uint32_t run = seg_start;
+        bool hp = have_prev, ph = prev_heavy;
+        uint32_t pw = prev_win;
+#pragma unroll 8
+        for (int k = 0; k < PER; k++)
+        {
+            const uint32_t c = __ldcg(hist + b0 + k);
+            if (c)
+            {
+                const bool heavy = c > (uint32_t)(kMsdCap - kMsdWindow);
+                const uint32_t win = run / kMsdWindow;
+                if (!hp || heavy || ph || win != pw) opens++;
+                hp = true;
+                ph = heavy;
+                pw = win;
+            }
+            run += c;
+        }
+    }
+    uint32_t n_ranges = 0;
+    const uint32_t first_range = msd_block_scan<kMsdPlanThreads>(opens, s_warp, &n_ranges);
+
+    // ---- range ids and range starts ----
+    {
+        uint32_t run = seg_start, next = first_range; // id of the next range to open
+        bool hp = have_prev, ph = prev_heavy;
+        uint32_t pw = prev_win;
+#pragma unroll 8
+        for (int k = 0; k < PER; k++)
+        {
+            const uint32_t c = __ldcg(hist + b0 + k);
+            uint32_t id = next ? next - 1 : 0; // empty bins: never looked up
+            if (c)
+            {
+                const bool heavy = c > (uint32_t)(kMsdCap - kMsdWindow);
+                const uint32_t win = run / kMsdWindow;
+                if (!hp || heavy || ph || win != pw)
+                {
+                    if (next < (uint32_t)kMsdMaxRanges) range_start[next] = run;
+                    next++;
+                }
+                id = next - 1;
+                hp = true;
+                ph = heavy;
+                pw = win;
+            }
+            range_of_bin[b0 + k] = (uint16_t)min(id, (uint32_t)kMsdMaxRanges - 1u);
+            run += c;
+        }
+    }
+    if (tid == 0)
+    {
+        const bool fallback = max_bin > (uint32_t)kMsdCap || n_ranges > (uint32_t)kMsdMaxRanges || total != T || n_ranges == 0;
+        ctl[kMsdCtlRanges] = n_ranges;
+        ctl[kMsdCtlFallback] = fallback ? 1u : 0u;
+        if (n_ranges <= (uint32_t)kMsdMaxRanges) range_start[n_ranges] = T;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. partition + range-local sorts
+// ---------------------------------------------------------------------------------------------------------------
+struct MsdSmem
+{
+    union
+    {
+        uint2 kv[kMsdCap]; // partition: (key, input position | range id << 21) by slot
+        struct
+        {
+            uint32_t key[kMsdCap];    // range-local sort: keys by position in the range (they stay put)
+            uint16_t id[kMsdCap];     // current order: positions in the range
+            uint16_t id_alt[kMsdCap];
+        } loc;
+    };
+    union
+    {
+        uint16_t cnt[kMsdWarps][kMsdMaxRanges]; // partition: per-warp running counts -> warp-exclusive offsets
+        uint2 tab[kMsdWarps][256];              // range-local passes: (.x running count -> offset, .y peer mask)
+    };
+    uint32_t base[kMsdMaxRanges]; // partition: slot base of a range in this CTA, then its global base; passes: digit bases
+    uint32_t scan[40];
+};
+
+struct MsdJob
+{
+    uint32_t *keys_a, *keys_b, *vals_a, *vals_b; // input keys in keys_a; result in (keys_a, vals_a)
+    uint32_t* ctl;
+    uint32_t T;
+};
+
+__global__ void __launch_bounds__(kMsdThreads, 2) msd_sort_kernel(const MsdJob job)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MsdSmem& sm = *reinterpret_cast<MsdSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t cta = blockIdx.x, G = gridDim.x, T = job.T;
+    uint32_t* const ctl = job.ctl;
+    const uint32_t n_ranges = ctl[kMsdCtlRanges]; // written by the plan kernel (an earlier launch)
+    const uint16_t* __restrict__ range_of_bin = reinterpret_cast<const uint16_t*>(ctl + kMsdCtlRangeOfBin);
+    const uint32_t* __restrict__ range_start = ctl + kMsdCtlRangeStart;
+    uint32_t* const mat = ctl + kMsdCtlMat;
+    uint32_t gen = 0;
+
+    const uint32_t ipt = (T + G * kMsdThreads - 1) / (G * kMsdThreads); // <= kMsdIpt (checked by the host)
+    const uint32_t chunk = kMsdThreads * ipt;
+    const uint32_t cta_base = cta * chunk;
+    const uint32_t cta_valid = cta_base < T ? min(chunk, T - cta_base) : 0u;
+    const uint32_t warp_base = cta_base + warp * (32 * ipt);
+
+    // ================= stable partition by range id =================
+    uint32_t key[kMsdIpt];
+    uint16_t rid[kMsdIpt], rank[kMsdIpt];
+#pragma unroll
+    for (int j = 0; j < kMsdIpt; j++)
+    {
+        const uint32_t i = warp_base + j * 32 + lane;
+        const bool valid = (uint32_t)j < ipt && i < T;
+        key[j] = valid ? __ldg(job.keys_a + i) : 0xffffffffu;
+        rid[j] = valid ? range_of_bin[key[j] >> kMsdFineShift] : (uint16_t)0;
+    }
+    for (uint32_t i = tid; i < (uint32_t)(kMsdWarps * kMsdMaxRanges / 2); i += kMsdThreads)
+        reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
+    __syncthreads();
+    // in-warp stable ranking by ballots over the bits of the range id: constant cost, no shared-memory atomics
+    uint16_t* my_cnt = sm.cnt[warp];
+#pragma unroll
+    for (int j = 0; j < kMsdIpt; j++)
+    {
+        if ((uint32_t)j < ipt) // warp-uniform
+        {
+            const uint32_t i = warp_base + j * 32 + lane;
+            const bool valid = i < T;
+            const uint32_t r = rid[j];
+            uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int b = 0; b < kMsdRangeBits; b++)
+            {
+                const bool bit = (r >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+            const uint32_t lower = __popc(peers & lanemask_lt());
+            const int leader = peers ? __ffs(peers) - 1 : 0;
+            uint32_t prev = 0;
+            if (valid && (int)lane == leader)
+            {
+                prev = my_cnt[r];
+                my_cnt[r] = (uint16_t)(prev + __popc(peers));
+            }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            rank[j] = (uint16_t)(prev + lower);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // per-range CTA totals -> counts matrix; warp-exclusive offsets; slot bases (two consecutive ranges per thread)
+    {
+        uint32_t tot[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            const uint32_t r = 2 * tid + q;
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kMsdWarps; w++)
+            {
+                const uint32_t c = sm.cnt[w][r];
+                sm.cnt[w][r] = (uint16_t)run;
+                run += c;
+            }
+            tot[q] = run;
+            if (r < n_ranges) mat[(size_t)r * G + cta] = run;
+        }
+        uint32_t all = 0;
+        const uint32_t ex = msd_block_scan<kMsdThreads>(tot[0] + tot[1], sm.scan, &all);
+        sm.base[2 * tid] = ex;
+        sm.base[2 * tid + 1] = ex + tot[0];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kMsdIpt; j++)
+    {
+        const uint32_t i = warp_base + j * 32 + lane;
+        if ((uint32_t)j < ipt && i < T)
+        {
+            const uint32_t r = rid[j];
+            sm.kv[sm.base[r] + my_cnt[r] + rank[j]] = make_uint2(key[j], i | (r << kMsdValBits));
+        }
+    }
+    grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+    // one warp scans each range row of the counts matrix (exclusive prefix over CTAs)
+    for (uint32_t r = cta + warp * G; r < n_ranges; r += G * kMsdWarps)
+    {
+        uint32_t* row = mat + (size_t)r * G;
+        uint32_t v[kMsdRowSeg];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < kMsdRowSeg; k++)
+        {
+            const uint32_t c = lane * kMsdRowSeg + k;
+            v[k] = c < G ? __ldcg(row + c) : 0u;
+            sum += v[k];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += n;
+        }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int k = 0; k < kMsdRowSeg; k++)
+        {
+            const uint32_t c = lane * kMsdRowSeg + k;
+            if (c < G) row[c] = run;
+            run += v[k];
+        }
+    }
+    grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+    // global base of every range for this CTA's keys: range start + keys of the CTAs before it - local slot base
+    {
+        uint32_t gb[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            const uint32_t r = 2 * tid + q;
+            gb[q] = r < n_ranges ? range_start[r] + __ldcg(mat + (size_t)r * G + cta) - sm.base[r] : 0u;
+        }
+        __syncthreads();
+        sm.base[2 * tid] = gb[0];
+        sm.base[2 * tid + 1] = gb[1];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kMsdIpt; k++)
+    {
+        const uint32_t s = tid + k * kMsdThreads;
+        if (s < cta_valid)
+        {
+            const uint2 e = sm.kv[s];
+            const uint32_t dst = sm.base[e.y >> kMsdValBits] + s;
+            job.keys_b[dst] = e.x;
+            job.vals_b[dst] = e.y & ((1u << kMsdValBits) - 1u);
+        }
+    }
+    grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+
+    // ================= range-local stable sorts =================
+    const uint32_t lane_bit = 1u << lane;
+    for (uint32_t r = cta; r < n_ranges; r += G)
+    {
+        const uint32_t a = range_start[r];
+        const uint32_t n = min(range_start[r + 1] - a, (uint32_t)kMsdCap);
+        __syncthreads(); // the previous range (or the partition) is done with the shared arrays
+        for (uint32_t e = tid; e < n; e += kMsdThreads)
+        {
+            sm.loc.key[e] = __ldcg(job.keys_b + a + e);
+            sm.loc.id[e] = (uint16_t)e;
+        }
+        const uint32_t wchunk = (((n + kMsdWarps - 1) / kMsdWarps) + 31u) & ~31u; // entries per warp, whole steps of 32
+        uint2* my_tab = sm.tab[warp];
+        for (int pass = 0; pass < 4; pass++)
+        {
+            const uint16_t* src = (pass & 1) ? sm.loc.id_alt : sm.loc.id;
+            uint16_t* dst = (pass & 1) ? sm.loc.id : sm.loc.id_alt;
+            const uint32_t shift = 8u * pass;
+            for (uint32_t i = tid; i < (uint32_t)(kMsdWarps * 256); i += kMsdThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
+            __syncthreads();
+            uint16_t rk[kMsdIpt];
+#pragma unroll
+            for (int s = 0; s < kMsdIpt; s++)
+            {
+                if ((uint32_t)s * 32u < wchunk) // warp-uniform
+                {
+                    const uint32_t i = warp * wchunk + s * 32 + lane;
+                    const bool valid = i < n && s * 32u + lane < wchunk;
+                    const uint32_t dgt = valid ? (sm.loc.key[src[i]] >> shift) & 255u : 0u;
+                    if (valid) atomicOr(&my_tab[dgt].y, lane_bit);
+                    __syncwarp();
+                    uint2 e = make_uint2(0u, 0u);
+                    if (valid) e = my_tab[dgt]; // (count before this step, peers of this step)
+                    const uint32_t lower = __popc(e.y & lanemask_lt());
+                    rk[s] = (uint16_t)(e.x + lower);
+                    __syncwarp();
+                    if (valid && lower == 0) my_tab[dgt] = make_uint2(e.x + __popc(e.y), 0u); // lowest lane closes the group
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // digit bases: exclusive over (digit, warp)
+            {
+                uint32_t tot = 0;
+                if (tid < 256)
+                {
+#pragma unroll
+                    for (int w = 0; w < kMsdWarps; w++)
+                    {
+                        const uint32_t c = sm.tab[w][tid].x;
+                        sm.tab[w][tid].x = tot;
+                        tot += c;
+                    }
+                }
+                uint32_t all = 0;
+                const uint32_t ex = msd_block_scan<kMsdThreads>(tot, sm.scan, &all);
+                if (tid < 256) sm.base[tid] = ex;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < kMsdIpt; s++)
+            {
+                if ((uint32_t)s * 32u < wchunk)
+                {
+                    const uint32_t i = warp * wchunk + s * 32 + lane;
+                    if (i < n && s * 32u + lane < wchunk)
+                    {
+                        const uint16_t idx = src[i];
+                        const uint32_t dgt = (sm.loc.key[idx] >> shift) & 255u;
+                        dst[sm.base[dgt] + my_tab[dgt].x + rk[s]] = idx;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // four passes: the order is back in loc.id; keys from shared memory, values from the partition output
+        for (uint32_t e = tid; e < n; e += kMsdThreads)
+        {
+            const uint32_t idx = sm.loc.id[e];
+            job.keys_a[a + e] = sm.loc.key[idx];
+            job.vals_a[a + e] = __ldcg(job.vals_b + a + idx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int g_msd_grid = 0;
+
+cudaError_t msd_sort_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(msd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdSmem));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0, dev = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msd_sort_kernel, kMsdThreads, sizeof(MsdSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    g_msd_grid = std::min(sms * std::min(per_sm, 2), 32 * kMsdRowSeg);
+    return cudaSuccess;
+}
+
+uint32_t msd_sort_capacity()
+{
+    const uint64_t cap = (uint64_t)g_msd_grid * kMsdCap;
+    return (uint32_t)std::min<uint64_t>(cap, (1u << kMsdValBits) - 1u);
+}
+size_t msd_sort_ctl_words() { return kMsdCtlMat + (size_t)kMsdMaxRanges * 32 * kMsdRowSeg; }
+
+// Enqueue histogram + plan. ctl: msd_sort_ctl_words() words. Afterwards ctl[2] = number of ranges and ctl[3] = 1 when
+// the input needs the 4-pass sort instead (read them back before calling launch_msd_sort).
+cudaError_t launch_msd_plan(const uint32_t* keys, uint32_t T, uint32_t* ctl, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(ctl, 0, (kMsdCtlHist + kMsdFineBins) * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    msd_fine_hist_kernel<<<148 * 4, 256, 0, s>>>(keys, T, ctl + kMsdCtlHist);
+    msd_plan_kernel<<<1, kMsdPlanThreads, 0, s>>>(ctl, T);
+    return cudaGetLastError();
+}
+
+// Sort (keys_a, identity values) -> (keys_a, vals_a) with the plan in ctl; keys_b / vals_b are scratch.
+cudaError_t launch_msd_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
+                            uint32_t* ctl, cudaStream_t s)
+{
+    if (g_msd_grid == 0 || T == 0 || T > msd_sort_capacity()) return cudaErrorInvalidValue;
+    MsdJob job{keys_a, keys_b, vals_a, vals_b, ctl, T};
+    void* args[] = {&job};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(msd_sort_kernel), dim3(g_msd_grid),
+                                       dim3(kMsdThreads), args, sizeof(MsdSmem), s);
+}
+
+} // namespace oibvh

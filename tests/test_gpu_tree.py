@@ -1,4 +1,5 @@
 """GPU parity, build/refit/transform: the CUDA path through the C ABI against the CPU oracle, bit-exact."""
+import os
 import numpy as np
 import pytest
 
@@ -222,3 +223,25 @@ def test_many_small_trees_in_one_launch(ctx, port):
         w2 = port.build(port.transform_positions(p, M), f, m.m_aabb)  # keys from the moved vertices, original mesh box
         assert np.array_equal(t.download()["perm"], w2["perm"])
         assert_bit_equal(t.download()["nodes"], w2["nodes"], "rebuild after the transform")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("OIBVH_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental MSD sort (sort_msd.cu): set OIBVH_TEST_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("T", [5000, 65536, 200000, 1048576])
+def test_experimental_msd_sort_builds_the_same_tree(ctx, port, T):
+    """OIBVH_SORT_MSD=1: equal-count MSD partition + range-local sorts must give the 4-pass sort's permutation"""
+    nu = max(16, int((T / 2) ** 0.5) + 2)
+    pos, faces = meshgen.blob(nu, nu, seed=7)
+    faces = meshgen.shuffle_faces(faces)[:T]
+    want = port.build(pos, faces, port.mesh_aabb(pos))
+    os.environ["OIBVH_SORT_MSD"] = "1"
+    try:
+        t = ob.OibvhTree(ob.Mesh(pos, faces), ctx=ctx)
+        t.build()
+        got = t.download()
+    finally:
+        os.environ.pop("OIBVH_SORT_MSD", None)
+    assert np.array_equal(got["perm"], want["perm"])
+    assert np.array_equal(got["nodes"].view(np.uint32), want["nodes"].view(np.uint32))
+    t.close()
