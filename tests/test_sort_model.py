@@ -40,3 +40,21 @@ def test_model_ties_small_inputs_and_fallback():
     sizes = np.bincount(plan[3][plan[0]])
     assert sizes.max() <= 4096 and 3500 in sizes
     assert sort_model.msd_equal_count_sort(np.full(5000, 123 << 14, np.uint32), window=1024, capacity=4096) is None
+
+
+def test_transcribed_kernels_equal_stable_sort():
+    """thread-level transcription of sort_msd.cu (tools/msd_kernel_emulation.py): plan == model, result == stable sort"""
+    import msd_kernel_emulation as emu
+    rng = np.random.default_rng(9)
+    cases = [rng.integers(0, 1 << 30, 6000).astype(np.uint32),
+             ((rng.integers(0, 30, 5000).astype(np.uint32) << 22) | rng.integers(0, 3, 5000).astype(np.uint32)),
+             rng.integers(0, 1 << 30, 300).astype(np.uint32)]
+    for keys in cases:
+        hist = np.bincount(keys >> 14, minlength=emu.BINS)
+        n, fallback, range_of_bin, range_start = emu.plan_kernel(hist, len(keys))
+        fine, h, start, want_rob = sort_model.plan_ranges(keys, 16, emu.WIN, emu.CAP)
+        assert not fallback and np.array_equal(range_of_bin[h > 0], want_rob[h > 0])
+        k, v = emu.sort(keys, G=3)
+        want = np.argsort(keys, kind="stable")
+        assert np.array_equal(v, want) and np.array_equal(k, keys[want])
+    assert emu.sort(np.full(9000, 77 << 14, np.uint32)) is None  # one bin above the range capacity: fallback
