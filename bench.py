@@ -178,11 +178,24 @@ def cpu_frame_port(port, pos, faces, posB, aabb):
     return (time.perf_counter() - t0) * 1e3, len(pairs), ncand
 
 
+def host_info():
+    """nproc and CPU model of the box the CPU baseline ran on"""
+    model = None
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.lower().startswith("model name"):
+                model = l.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model, "threads_used": 1}
+
+
 def cpu_baseline_port(pos, faces, posB, aabb, frames=3):
     import oracle
     port = oracle.Port()
     ms = [cpu_frame_port(port, pos, faces, posB, aabb) for _ in range(frames)]
-    return {"value": float(np.median([m[0] for m in ms])), "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": float(np.median([m[0] for m in ms])), "unit": UNIT, "cores": 1, "kind": "port", "host": host_info(),
             "sample": f"full workload (2 x {len(faces)} tris), median of {frames} frames, single thread "
                       "(the reference CPU path is single-threaded)", "pairs": ms[0][1], "candidates": ms[0][2]}
 
@@ -342,7 +355,8 @@ def run_reference_arm(args):
     line.update({"value": value, "ms_per_step": value,
                  "config": {"workload": "two 2^20-triangle synthetic blobs, build x2 + refit x2 + detect per frame, "
                                         "reference CPU path (SimpleBVH + SimpleCollide)"},
-                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                                  "host": host_info()},
                  "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     line.update(extra)
     print(json.dumps(line), flush=True)
