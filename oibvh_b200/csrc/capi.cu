@@ -741,30 +741,46 @@ static bool msd_sort_requested()
     return e != nullptr && e[0] == '1';
 }
 
-// EXPERIMENTAL path of oibvh_tree_build: keys are in tree->keys_a. *sorted = true when (keys_a, vals_a) hold the result.
-static int msd_sort_try(oibvh_tree* tree, bool* sorted)
+// EXPERIMENTAL path (OIBVH_SORT_MSD=1): the keys of every tree are in keys_a. *sorted = true when the launches that
+// leave the result in (keys_a, vals_a) have been enqueued; false = use the 4-pass cooperative sort. Nothing is read
+// back (the plan's fallback is taken inside the kernel), so it is capturable -- the control blocks must then exist
+// already (one eager call first, like every *_many entry point).
+static int msd_sort_try(oibvh_tree* const* trees, uint32_t n, bool* sorted)
 {
     *sorted = false;
-    oibvh_ctx* ctx = tree->ctx;
+    oibvh_ctx* ctx = trees[0]->ctx;
     static bool configured = false;
     if (!configured)
     {
+        if (ctx->capturing) return OIBVH_OK;
         CU(msd_sort_configure());
         configured = true;
     }
-    if (tree->T > msd_sort_capacity()) return OIBVH_OK;
-    if (!tree->msd_ctl)
+    if (n == 0 || n > 4) return OIBVH_OK;
+    uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
+    const uint32_t* kin[4];
+    for (uint32_t i = 0; i < n; i++)
     {
-        int rc = dev_alloc(&tree->msd_ctl, msd_sort_ctl_words());
-        if (rc) return rc;
+        oibvh_tree* t = trees[i];
+        if (t->T > msd_sort_capacity() / n) return OIBVH_OK;
+        if (!t->msd_ctl)
+        {
+            if (ctx->capturing) return OIBVH_OK;
+            int rc = dev_alloc(&t->msd_ctl, msd_sort_ctl_words());
+            if (rc) return rc;
+        }
+        ka[i] = t->keys_a; kb[i] = t->keys_b; va[i] = t->vals_a; vb[i] = t->vals_b; ctl[i] = t->msd_ctl; T[i] = t->T;
+        kin[i] = t->keys_a;
     }
-    CU(launch_msd_plan(tree->keys_a, tree->T, tree->msd_ctl, ctx->stream));
-    count_launch(ctx, 2);
-    uint32_t head[4] = {0, 0, 0, 1};
-    CU(cudaMemcpyAsync(head, tree->msd_ctl, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (head[3] != 0 || head[2] == 0) return OIBVH_OK; // a bin above the range capacity / too many ranges: 4-pass sort
-    CU(launch_msd_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->msd_ctl, ctx->stream));
+    CU(launch_msd_plan_many(n, kin, T, ctl, ctx->stream));
+    count_launch(ctx, n + 1);
+    cudaError_t e = launch_msd_sort_many(n, ka, kb, va, vb, T, ctl, ctx->stream);
+    if (e == cudaErrorInvalidValue)
+    {
+        cudaGetLastError();
+        return OIBVH_OK; // sizes do not fit the CTA ranges: 4-pass path
+    }
+    CU(e);
     count_launch(ctx);
     *sorted = true;
     return OIBVH_OK;
@@ -800,11 +816,11 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
         CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
         count_launch(ctx);
         bool sorted = false;
-        if (msd_sort_requested() && !ctx->capturing)
+        if (msd_sort_requested())
         {
-            // EXPERIMENTAL, opt-in (OIBVH_SORT_MSD=1): equal-count MSD partition + range-local sorts (sort_msd.cu).
-            // The plan is read back (one host sync) to decide between it and the 4-pass sort; not capturable.
-            int rc = msd_sort_try(tree, &sorted);
+            // EXPERIMENTAL, opt-in (OIBVH_SORT_MSD=1): equal-count MSD partition + range-local sorts (sort_msd.cu)
+            oibvh_tree* one[1] = {tree};
+            int rc = msd_sort_try(one, 1, &sorted);
             if (rc) return rc;
         }
         if (!sorted)
@@ -968,8 +984,14 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    cudaError_t e = launch_coop_sort_many(n, ka, kb, va, vb, T, ctl, s);
-    if (e == cudaErrorInvalidValue)
+    bool msd_done = false;
+    if (msd_sort_requested())
+    {
+        int rc = msd_sort_try(trees, n, &msd_done); // EXPERIMENTAL, opt-in (sort_msd.cu)
+        if (rc) return rc;
+    }
+    const cudaError_t e = msd_done ? cudaSuccess : launch_coop_sort_many(n, ka, kb, va, vb, T, ctl, s);
+    if (!msd_done && e == cudaErrorInvalidValue)
     {
         // very unequal sizes: sort one by one (keys are already computed)
         cudaGetLastError();
@@ -985,7 +1007,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
                 return fail(OIBVH_ERR_INTERNAL, "build_many: tree %u does not fit the cooperative sort", i);
         }
     }
-    else
+    else if (!msd_done)
     {
         CU(e);
         count_launch(ctx);

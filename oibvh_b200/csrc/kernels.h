@@ -45,14 +45,16 @@ cudaError_t launch_coop_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t*
 cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
                              uint32_t* ctl, cudaStream_t s);
 // EXPERIMENTAL (sort_msd.cu, off by default): one stable partition by equal-count key ranges + range-local sorts in
-// shared memory. launch_msd_plan enqueues histogram + plan into ctl (msd_sort_ctl_words() words); ctl[2] = ranges,
-// ctl[3] = 1 if the input needs the 4-pass sort; launch_msd_sort then sorts (keys_a, identity) -> (keys_a, vals_a).
+// shared memory, with the 4-pass LSD sort built in as the fallback the plan can ask for. launch_msd_plan_many enqueues
+// histograms + plans into ctl[i] (msd_sort_ctl_words() words each); launch_msd_sort_many then sorts
+// (keys_a[i], identity) -> (keys_a[i], vals_a[i]) for n <= 4 arrays in one cooperative launch. Nothing is read back.
 cudaError_t msd_sort_configure();
 uint32_t msd_sort_capacity();
 size_t msd_sort_ctl_words();
-cudaError_t launch_msd_plan(const uint32_t* keys, uint32_t T, uint32_t* ctl, cudaStream_t s);
-cudaError_t launch_msd_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
-                            uint32_t* ctl, cudaStream_t s);
+cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const uint32_t* T, uint32_t* const* ctl,
+                                 cudaStream_t s);
+cudaError_t launch_msd_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
+                                 uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s);
 cudaError_t tree_emit_configure();
 // arrival counters of the hierarchical top-of-tree completion (zeroed once; the kernel re-arms them)
 size_t emit_counter_words(uint32_t T);

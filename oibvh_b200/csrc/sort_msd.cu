@@ -1,6 +1,7 @@
-// EXPERIMENTAL -- off by default (OIBVH_SORT_MSD=1 selects it in oibvh_tree_build for single-wave sizes outside a
-// graph capture). Written against the executable model tools/sort_model.py; it has been compiled for
-// sm_100a but NOT yet run on a GPU: the shipped path is the cooperative 4-pass LSD sort in sort_coop.cu.
+// EXPERIMENTAL -- off by default (OIBVH_SORT_MSD=1 selects it in oibvh_tree_build / oibvh_tree_build_many for
+// single-wave sizes). Written against the executable model tools/sort_model.py and the thread-level transcription
+// tools/msd_kernel_emulation.py; it has been compiled for sm_100a but NOT yet run on a GPU: the
+// shipped path is the cooperative 4-pass LSD sort in sort_coop.cu.
 //
 // Stable sort of (30-bit Morton key, face id) with ONE global data movement instead of four:
 //   1. msd_fine_hist_kernel   histogram of the top 16 key bits (65 536 bins)
@@ -8,7 +9,9 @@
 //                             range when it starts in another kMsdWindow-key output window than the non-empty bin
 //                             before it, or when it or that bin is heavy (> kMsdCap - kMsdWindow keys); writes the
 //                             bin -> range table, the range starts, and a fallback flag (a bin above kMsdCap keys, or
-//                             more than kMsdMaxRanges ranges) that sends the caller to the 4-pass sort
+//                             more than kMsdMaxRanges ranges) that makes the sort kernel take its built-in 4-pass
+//                             LSD path instead (msd_lsd4_fallback: the algorithm of sort_coop.cu), so no host
+//                             decision is needed and the whole build stays graph-capturable
 //   3. msd_sort_kernel        cooperative: stable partition of the input by range id (per-CTA ranking, counts matrix,
 //                             row scan between two grid barriers, as in sort_coop.cu but the "digit" is the range id),
 //                             then every range is sorted stably by its full key inside one CTA's shared memory
@@ -95,8 +98,15 @@ __device__ __forceinline__ uint32_t msd_block_scan(uint32_t v, uint32_t* s_warp,
 // ---------------------------------------------------------------------------------------------------------------
 // 2. plan: one CTA, thread t owns the 64 consecutive bins [64 t, 64 t + 64)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(uint32_t* __restrict__ ctl, uint32_t T)
+struct MsdPlanJobs
 {
+    uint32_t* ctl[4];
+    uint32_t T[4];
+};
+__global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlanJobs pj)
+{
+    uint32_t* __restrict__ ctl = pj.ctl[blockIdx.x];
+    const uint32_t T = pj.T[blockIdx.x];
     constexpr int PER = kMsdFineBins / kMsdPlanThreads; // 64
     __shared__ uint32_t s_warp[40];
     __shared__ uint32_t s_last_start[kMsdPlanThreads]; // start of the thread's last non-empty bin
@@ -246,15 +256,176 @@ struct MsdJob
     uint32_t *keys_a, *keys_b, *vals_a, *vals_b; // input keys in keys_a; result in (keys_a, vals_a)
     uint32_t* ctl;
     uint32_t T;
+    uint32_t cta0, ncta; // this job's CTA range inside the launch (several trees side by side, per-job barriers)
+};
+constexpr int kMsdMaxJobs = 4;
+struct MsdJobs
+{
+    MsdJob j[kMsdMaxJobs];
+    uint32_t n;
 };
 
-__global__ void __launch_bounds__(kMsdThreads, 2) msd_sort_kernel(const MsdJob job)
+// ---------------------------------------------------------------------------------------------------------------
+// Built-in fallback: the stable 4-pass LSD sort of sort_coop.cu (8-bit digits, peer-mask ranking, counts matrix + row
+// scan between grid barriers) on this job's CTAs, for inputs whose plan asks for it. Uses the same shared arrays:
+// kv = reorder buffer, tab = ranking tables, base[0..255] = global digit bases. Counts matrix: ctl + kMsdCtlMat
+// (256 x G words), digit totals: ctl + kMsdCtlRangeStart (256 words). Result in (keys_a, vals_a).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void msd_lsd4_fallback(MsdSmem& sm, const MsdJob& job, uint32_t cta, uint32_t G, uint32_t& gen)
+{
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t T = job.T;
+    uint32_t* const ctl = job.ctl;
+    uint32_t* const mat = ctl + kMsdCtlMat;
+    uint32_t* const totals = ctl + kMsdCtlRangeStart;
+    const uint32_t ipt = (T + G * kMsdThreads - 1) / (G * kMsdThreads);
+    const uint32_t chunk = kMsdThreads * ipt;
+    const uint32_t cta_base = cta * chunk;
+    const uint32_t cta_valid = cta_base < T ? min(chunk, T - cta_base) : 0u;
+    const uint32_t warp_base = cta_base + warp * (32 * ipt);
+    uint32_t *kin = job.keys_a, *kout = job.keys_b, *vin = nullptr, *vout = job.vals_b;
+    for (int pass = 0; pass < 4; pass++)
+    {
+        const uint32_t shift = pass * 8;
+        uint32_t key[kMsdIpt];
+        uint16_t rank[kMsdIpt];
+#pragma unroll
+        for (int j = 0; j < kMsdIpt; j++)
+        {
+            const uint32_t i = warp_base + j * 32 + lane;
+            const bool valid = (uint32_t)j < ipt && i < T;
+            key[j] = valid ? __ldcg(kin + i) : 0xffffffffu;
+        }
+        for (uint32_t i = tid; i < (uint32_t)(kMsdWarps * 256); i += kMsdThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
+        __syncthreads();
+        uint2* my_tab = sm.tab[warp];
+        const uint32_t lane_bit = 1u << lane;
+#pragma unroll
+        for (int j = 0; j < kMsdIpt; j++)
+        {
+            if ((uint32_t)j < ipt) // warp-uniform
+            {
+                const uint32_t i = warp_base + j * 32 + lane;
+                const bool valid = i < T;
+                const uint32_t d = (key[j] >> shift) & 255u;
+                if (valid) atomicOr(&my_tab[d].y, lane_bit);
+                __syncwarp();
+                uint2 e = make_uint2(0u, 0u);
+                if (valid) e = my_tab[d];
+                const uint32_t lower = __popc(e.y & lanemask_lt());
+                rank[j] = (uint16_t)(e.x + lower);
+                __syncwarp();
+                if (valid && lower == 0) my_tab[d] = make_uint2(e.x + __popc(e.y), 0u);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        uint32_t cta_count = 0;
+        if (tid < 256)
+        {
+#pragma unroll
+            for (int w = 0; w < kMsdWarps; w++)
+            {
+                const uint32_t c = sm.tab[w][tid].x;
+                sm.tab[w][tid].x = cta_count;
+                cta_count += c;
+            }
+            mat[(size_t)tid * G + cta] = cta_count;
+        }
+        uint32_t all = 0;
+        const uint32_t digit_base = msd_block_scan<kMsdThreads>(cta_count, sm.scan, &all); // threads >= 256 add 0
+        if (tid < 256) sm.base[256 + tid] = digit_base; // local slot base of every digit
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kMsdIpt; j++)
+        {
+            const uint32_t i = warp_base + j * 32 + lane;
+            if ((uint32_t)j < ipt && i < T)
+            {
+                const uint32_t val = vin ? __ldcg(vin + i) : i;
+                const uint32_t d = (key[j] >> shift) & 255u;
+                sm.kv[sm.base[256 + d] + my_tab[d].x + rank[j]] = make_uint2(key[j], val);
+            }
+        }
+        grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+        for (uint32_t r = cta + warp * G; r < 256u; r += G * kMsdWarps)
+        {
+            uint32_t* row = mat + (size_t)r * G;
+            uint32_t v[kMsdRowSeg];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < kMsdRowSeg; k++)
+            {
+                const uint32_t c = lane * kMsdRowSeg + k;
+                v[k] = c < G ? __ldcg(row + c) : 0u;
+                sum += v[k];
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += n;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < kMsdRowSeg; k++)
+            {
+                const uint32_t c = lane * kMsdRowSeg + k;
+                if (c < G) row[c] = run;
+                run += v[k];
+            }
+            if (lane == 31) totals[r] = inc;
+        }
+        grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+        {
+            const uint32_t tot = tid < 256 ? __ldcg(totals + tid) : 0u;
+            const uint32_t col = tid < 256 ? __ldcg(mat + (size_t)tid * G + cta) : 0u;
+            uint32_t sum_all = 0;
+            const uint32_t ex = msd_block_scan<kMsdThreads>(tot, sm.scan, &sum_all);
+            if (tid < 256) sm.base[tid] = ex + col - sm.base[256 + tid]; // global base - local slot base
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kMsdIpt; k++)
+        {
+            const uint32_t s = tid + k * kMsdThreads;
+            if (s < cta_valid)
+            {
+                const uint2 e = sm.kv[s];
+                const uint32_t dst = sm.base[(e.x >> shift) & 255u] + s;
+                kout[dst] = e.x;
+                vout[dst] = e.y;
+            }
+        }
+        grid_sync(ctl + kMsdCtlBarrier, ++gen, ctl + kMsdCtlFail, G);
+        uint32_t* nk = kout;
+        uint32_t* nv = vout;
+        kout = (nk == job.keys_b) ? job.keys_a : job.keys_b;
+        vout = (nv == job.vals_b) ? job.vals_a : job.vals_b;
+        kin = nk;
+        vin = nv;
+    }
+}
+
+__global__ void __launch_bounds__(kMsdThreads, 2) msd_sort_kernel(const MsdJobs jobs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MsdSmem& sm = *reinterpret_cast<MsdSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const uint32_t cta = blockIdx.x, G = gridDim.x, T = job.T;
+    uint32_t ji = 0;
+#pragma unroll
+    for (int i = 1; i < kMsdMaxJobs; i++)
+        if ((uint32_t)i < jobs.n && blockIdx.x >= jobs.j[i].cta0) ji = i;
+    const MsdJob& job = jobs.j[ji];
+    const uint32_t cta = blockIdx.x - job.cta0, G = job.ncta, T = job.T;
     uint32_t* const ctl = job.ctl;
+    if (ctl[kMsdCtlFallback] != 0) // the plan (an earlier launch) asks for the 4-pass sort: uniform over the job's CTAs
+    {
+        uint32_t gen0 = 0;
+        msd_lsd4_fallback(sm, job, cta, G, gen0);
+        return;
+    }
     const uint32_t n_ranges = ctl[kMsdCtlRanges]; // written by the plan kernel (an earlier launch)
     const uint16_t* __restrict__ range_of_bin = reinterpret_cast<const uint16_t*>(ctl + kMsdCtlRangeOfBin);
     const uint32_t* __restrict__ range_start = ctl + kMsdCtlRangeStart;
@@ -520,26 +691,49 @@ uint32_t msd_sort_capacity()
 }
 size_t msd_sort_ctl_words() { return kMsdCtlMat + (size_t)kMsdMaxRanges * 32 * kMsdRowSeg; }
 
-// Enqueue histogram + plan. ctl: msd_sort_ctl_words() words. Afterwards ctl[2] = number of ranges and ctl[3] = 1 when
-// the input needs the 4-pass sort instead (read them back before calling launch_msd_sort).
-cudaError_t launch_msd_plan(const uint32_t* keys, uint32_t T, uint32_t* ctl, cudaStream_t s)
+// Enqueue, for n <= 4 trees, the histogram (one launch per tree, on `s`) and the plan (one launch, one CTA per tree).
+// ctl[i]: msd_sort_ctl_words() words per tree. Capturable: nothing is read back.
+cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const uint32_t* T, uint32_t* const* ctl,
+                                 cudaStream_t s)
 {
-    cudaError_t e = cudaMemsetAsync(ctl, 0, (kMsdCtlHist + kMsdFineBins) * sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
-    msd_fine_hist_kernel<<<148 * 4, 256, 0, s>>>(keys, T, ctl + kMsdCtlHist);
-    msd_plan_kernel<<<1, kMsdPlanThreads, 0, s>>>(ctl, T);
+    if (n == 0 || n > (uint32_t)kMsdMaxJobs) return cudaErrorInvalidValue;
+    MsdPlanJobs pj{};
+    for (uint32_t i = 0; i < n; i++)
+    {
+        cudaError_t e = cudaMemsetAsync(ctl[i], 0, (kMsdCtlHist + kMsdFineBins) * sizeof(uint32_t), s);
+        if (e != cudaSuccess) return e;
+        msd_fine_hist_kernel<<<148 * 4, 256, 0, s>>>(keys[i], T[i], ctl[i] + kMsdCtlHist);
+        pj.ctl[i] = ctl[i];
+        pj.T[i] = T[i];
+    }
+    msd_plan_kernel<<<n, kMsdPlanThreads, 0, s>>>(pj);
     return cudaGetLastError();
 }
 
-// Sort (keys_a, identity values) -> (keys_a, vals_a) with the plan in ctl; keys_b / vals_b are scratch.
-cudaError_t launch_msd_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
-                            uint32_t* ctl, cudaStream_t s)
+// Sort n <= 4 arrays (keys_a[i], identity values) -> (keys_a[i], vals_a[i]) with the plans in ctl[i], in ONE
+// cooperative launch: CTA ranges side by side in proportion to the sizes, per-job grid barriers. Returns
+// cudaErrorInvalidValue when an array does not fit its CTA range (the caller then uses the 4-pass path).
+cudaError_t launch_msd_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
+                                 uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s)
 {
-    if (g_msd_grid == 0 || T == 0 || T > msd_sort_capacity()) return cudaErrorInvalidValue;
-    MsdJob job{keys_a, keys_b, vals_a, vals_b, ctl, T};
-    void* args[] = {&job};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(msd_sort_kernel), dim3(g_msd_grid),
-                                       dim3(kMsdThreads), args, sizeof(MsdSmem), s);
+    if (g_msd_grid == 0 || n == 0 || n > (uint32_t)kMsdMaxJobs) return cudaErrorInvalidValue;
+    const uint32_t G = (uint32_t)g_msd_grid;
+    MsdJobs jobs{};
+    jobs.n = n;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += T[i];
+    uint32_t next = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint32_t ncta = (i + 1 == n) ? G - next : (uint32_t)std::max<uint64_t>(1, (uint64_t)G * T[i] / total);
+        if (next + ncta > G || ncta == 0) return cudaErrorInvalidValue;
+        if (T[i] == 0 || T[i] > (uint64_t)ncta * kMsdCap || T[i] >= (1u << kMsdValBits)) return cudaErrorInvalidValue;
+        jobs.j[i] = MsdJob{keys_a[i], keys_b[i], vals_a[i], vals_b[i], ctl[i], T[i], next, ncta};
+        next += ncta;
+    }
+    void* args[] = {&jobs};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(msd_sort_kernel), dim3(G), dim3(kMsdThreads), args,
+                                       sizeof(MsdSmem), s);
 }
 
 } // namespace oibvh

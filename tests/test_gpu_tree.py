@@ -244,4 +244,22 @@ def test_experimental_msd_sort_builds_the_same_tree(ctx, port, T):
         os.environ.pop("OIBVH_SORT_MSD", None)
     assert np.array_equal(got["perm"], want["perm"])
     assert np.array_equal(got["nodes"].view(np.uint32), want["nodes"].view(np.uint32))
+    # two trees side by side in one launch (oibvh_tree_build_many), eagerly and replayed from a graph
+    os.environ["OIBVH_SORT_MSD"] = "1"
+    try:
+        t2 = ob.OibvhTree(ob.Mesh(pos, faces[::-1].copy()), ctx=ctx)
+        want2 = port.build(pos, faces[::-1].copy(), port.mesh_aabb(pos))
+        ob.build_many([t, t2])
+        ctx.capture_begin()
+        ob.build_many([t, t2])
+        g = ctx.capture_end()
+        g.launch()
+        ctx.synchronize()
+        a, b = t.download(), t2.download()
+        g.close()
+    finally:
+        os.environ.pop("OIBVH_SORT_MSD", None)
+    assert np.array_equal(a["perm"], want["perm"]) and np.array_equal(b["perm"], want2["perm"])
+    assert np.array_equal(b["nodes"].view(np.uint32), want2["nodes"].view(np.uint32))
     t.close()
+    t2.close()

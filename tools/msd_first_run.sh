@@ -11,4 +11,5 @@ timeout 300 python -m pytest tests/test_gpu_tree.py -k experimental_msd -m gpu -
 for v in 0 1; do
   echo "== OIBVH_SORT_MSD=$v"
   OIBVH_SORT_MSD=$v timeout 200 python tools/refit_bench.py 2>&1 | grep build
+  OIBVH_SORT_MSD=$v timeout 200 python tools/stage_bench.py --frames 30 --check 2>&1 | tail -7   # two-tree launch inside the frame graph
 done
