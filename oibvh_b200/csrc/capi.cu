@@ -759,10 +759,11 @@ static int msd_sort_try(oibvh_tree* const* trees, uint32_t n, bool* sorted)
     if (n == 0 || n > 4) return OIBVH_OK;
     uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
     const uint32_t* kin[4];
+    for (uint32_t i = 0; i < n; i++) T[i] = trees[i]->T;
+    if (!msd_sort_fits(n, T)) return OIBVH_OK;
     for (uint32_t i = 0; i < n; i++)
     {
         oibvh_tree* t = trees[i];
-        if (t->T > msd_sort_capacity() / n) return OIBVH_OK;
         if (!t->msd_ctl)
         {
             if (ctx->capturing) return OIBVH_OK;

@@ -50,6 +50,7 @@ cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_
 // (keys_a[i], identity) -> (keys_a[i], vals_a[i]) for n <= 4 arrays in one cooperative launch. Nothing is read back.
 cudaError_t msd_sort_configure();
 uint32_t msd_sort_capacity();
+bool msd_sort_fits(uint32_t n, const uint32_t* T); // do n arrays of these sizes fit one launch?
 size_t msd_sort_ctl_words();
 cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const uint32_t* T, uint32_t* const* ctl,
                                  cudaStream_t s);

@@ -713,24 +713,43 @@ cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const 
 // Sort n <= 4 arrays (keys_a[i], identity values) -> (keys_a[i], vals_a[i]) with the plans in ctl[i], in ONE
 // cooperative launch: CTA ranges side by side in proportion to the sizes, per-job grid barriers. Returns
 // cudaErrorInvalidValue when an array does not fit its CTA range (the caller then uses the 4-pass path).
-cudaError_t launch_msd_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
-                                 uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s)
+// CTA ranges of n jobs in proportion to their sizes; false when a job does not fit its range (chunk of at most kMsdCap
+// keys per CTA) or the packed position field
+static bool msd_split(uint32_t n, const uint32_t* T, uint32_t* cta0, uint32_t* ncta)
 {
-    if (g_msd_grid == 0 || n == 0 || n > (uint32_t)kMsdMaxJobs) return cudaErrorInvalidValue;
+    if (g_msd_grid == 0 || n == 0 || n > (uint32_t)kMsdMaxJobs) return false;
     const uint32_t G = (uint32_t)g_msd_grid;
-    MsdJobs jobs{};
-    jobs.n = n;
     uint64_t total = 0;
     for (uint32_t i = 0; i < n; i++) total += T[i];
+    if (total == 0) return false;
     uint32_t next = 0;
     for (uint32_t i = 0; i < n; i++)
     {
-        const uint32_t ncta = (i + 1 == n) ? G - next : (uint32_t)std::max<uint64_t>(1, (uint64_t)G * T[i] / total);
-        if (next + ncta > G || ncta == 0) return cudaErrorInvalidValue;
-        if (T[i] == 0 || T[i] > (uint64_t)ncta * kMsdCap || T[i] >= (1u << kMsdValBits)) return cudaErrorInvalidValue;
-        jobs.j[i] = MsdJob{keys_a[i], keys_b[i], vals_a[i], vals_b[i], ctl[i], T[i], next, ncta};
-        next += ncta;
+        const uint32_t c = (i + 1 == n) ? G - next : (uint32_t)std::max<uint64_t>(1, (uint64_t)G * T[i] / total);
+        if (next + c > G || c == 0) return false;
+        if (T[i] == 0 || T[i] > (uint64_t)c * kMsdCap || T[i] >= (1u << kMsdValBits)) return false;
+        cta0[i] = next;
+        ncta[i] = c;
+        next += c;
     }
+    return true;
+}
+bool msd_sort_fits(uint32_t n, const uint32_t* T)
+{
+    uint32_t a[kMsdMaxJobs], b[kMsdMaxJobs];
+    return msd_split(n, T, a, b);
+}
+
+cudaError_t launch_msd_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
+                                 uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s)
+{
+    uint32_t cta0[kMsdMaxJobs], ncta[kMsdMaxJobs];
+    if (!msd_split(n, T, cta0, ncta)) return cudaErrorInvalidValue;
+    const uint32_t G = (uint32_t)g_msd_grid;
+    MsdJobs jobs{};
+    jobs.n = n;
+    for (uint32_t i = 0; i < n; i++)
+        jobs.j[i] = MsdJob{keys_a[i], keys_b[i], vals_a[i], vals_b[i], ctl[i], T[i], cta0[i], ncta[i]};
     void* args[] = {&jobs};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(msd_sort_kernel), dim3(G), dim3(kMsdThreads), args,
                                        sizeof(MsdSmem), s);
