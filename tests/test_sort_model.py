@@ -58,3 +58,14 @@ def test_transcribed_kernels_equal_stable_sort():
         want = np.argsort(keys, kind="stable")
         assert np.array_equal(v, want) and np.array_equal(k, keys[want])
     assert emu.sort(np.full(9000, 77 << 14, np.uint32)) is None  # one bin above the range capacity: fallback
+
+
+def test_transcribed_fallback_equals_stable_sort():
+    """the 4-pass LSD path built into the experimental kernel (msd_lsd4_fallback), transcribed at thread level"""
+    import msd_kernel_emulation as emu
+    rng = np.random.default_rng(11)
+    for keys, G in ((rng.integers(0, 1 << 30, 4000).astype(np.uint32), 3),
+                    (np.full(2500, 77 << 14, np.uint32) | rng.integers(0, 4, 2500).astype(np.uint32), 2)):
+        k, v = emu.lsd4_fallback(keys, G)
+        want = np.argsort(keys, kind="stable")
+        assert np.array_equal(v, want) and np.array_equal(k, keys[want])

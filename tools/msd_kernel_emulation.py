@@ -172,3 +172,63 @@ def sort(keys, G=5):
     if fallback:
         return None
     return msd_sort_kernel(keys, G, n, range_of_bin, range_start)
+
+
+def lsd4_fallback(keys_a, G):
+    """transcription of msd_lsd4_fallback: four 8-bit passes, per-CTA ranking, counts matrix + row scan"""
+    T = len(keys_a)
+    ipt = (T + G * THREADS - 1) // (G * THREADS)
+    assert ipt <= IPT_MAX
+    chunk = THREADS * ipt
+    kin, vin = np.asarray(keys_a, np.uint32).copy(), None
+    for p in range(4):
+        shift = 8 * p
+        kout = np.zeros(T, np.uint32)
+        vout = np.zeros(T, np.uint32)
+        mat = np.zeros((256, G), np.int64)
+        state = []
+        for cta in range(G):
+            cta_base = cta * chunk
+            cta_valid = min(chunk, T - cta_base) if cta_base < T else 0
+            tab = np.zeros((WARPS, 256), np.int64)
+            items = []  # (warp, digit, rank, key, val) in (warp, item, lane) order
+            for w in range(WARPS):
+                warp_base = cta_base + w * (32 * ipt)
+                for j in range(ipt):
+                    lanes = [(l, warp_base + j * 32 + l) for l in range(32) if warp_base + j * 32 + l < T]
+                    dg = {l: (int(kin[i]) >> shift) & 255 for l, i in lanes}
+                    for l, i in lanes:
+                        d = dg[l]
+                        lower = sum(1 for m, _ in lanes if m < l and dg[m] == d)
+                        items.append((w, d, tab[w, d] + lower, int(kin[i]), int(vin[i]) if vin is not None else i))
+                    for d in set(dg.values()):
+                        tab[w, d] += sum(1 for v in dg.values() if v == d)
+            cta_count = np.zeros(256, np.int64)
+            for d in range(256):
+                run = 0
+                for w in range(WARPS):
+                    c = tab[w, d]
+                    tab[w, d] = run
+                    run += c
+                cta_count[d] = run
+                mat[d, cta] = run
+            local = np.cumsum(cta_count) - cta_count          # base[256 + d]
+            kv = [None] * max(cta_valid, 1)
+            for w, d, rk, k, v in items:
+                slot = local[d] + tab[w, d] + rk
+                assert kv[slot] is None
+                kv[slot] = (k, v)
+            state.append((cta_valid, local, kv))
+        totals = mat.sum(axis=1)
+        matp = np.cumsum(mat, axis=1) - mat
+        ex = np.cumsum(totals) - totals
+        for cta in range(G):
+            cta_valid, local, kv = state[cta]
+            base = ex + matp[:, cta] - local
+            for s in range(cta_valid):
+                k, v = kv[s]
+                dst = base[(k >> shift) & 255] + s
+                kout[dst] = k
+                vout[dst] = v
+        kin, vin = kout, vout
+    return kin, vin
