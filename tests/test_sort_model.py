@@ -69,3 +69,29 @@ def test_transcribed_fallback_equals_stable_sort():
         k, v = emu.lsd4_fallback(keys, G)
         want = np.argsort(keys, kind="stable")
         assert np.array_equal(v, want) and np.array_equal(k, keys[want])
+
+
+def test_model_property_random_distributions():
+    """hypothesis: for arbitrary key multisets the model either returns the stable-sort permutation or asks for the
+    fallback, and every planned range respects the capacity"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(min_value=1, max_value=4000), st.integers(min_value=1, max_value=30),
+           st.integers(min_value=0, max_value=2 ** 31 - 1), st.sampled_from([(256, 1024), (512, 2048), (1024, 2048)]))
+    def check(n, spread_bits, seed, wc):
+        window, capacity = wc
+        rng = np.random.default_rng(seed)
+        keys = (rng.integers(0, 1 << spread_bits, n).astype(np.uint32) << np.uint32(30 - spread_bits))
+        keys |= rng.integers(0, 1 << max(1, 30 - spread_bits), n).astype(np.uint32) & np.uint32(rng.integers(0, 1 << 14))
+        keys &= np.uint32((1 << 30) - 1)
+        perm = sort_model.msd_equal_count_sort(keys, n_chunks=int(rng.integers(1, 9)), window=window, capacity=capacity)
+        hist = np.bincount(keys >> 14, minlength=1 << 16)
+        if perm is None:
+            assert hist.max() > capacity
+            return
+        assert np.array_equal(perm, np.argsort(keys, kind="stable"))
+        plan = sort_model.plan_ranges(keys, 16, window, capacity)
+        assert np.bincount(plan[3][plan[0]]).max() <= capacity
+
+    check()
