@@ -117,15 +117,31 @@ __global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlan
     uint32_t* range_start = ctl + kMsdCtlRangeStart;
     const uint32_t b0 = tid * PER;
 
-    // ---- bin starts: exclusive prefix of the histogram ----
+    // The thread's 64 counts are read ONCE (sixteen 128-bit loads) and parked in shared memory as 16-bit values,
+    // transposed (count k of thread t at [k][t]: conflict-free), clamped to 16 bits (a count that does not fit is far
+    // above kMsdCap and raises the fallback through max_bin): the walks below never touch global memory again.
+    // (Four walks of 64 scalar global loads each were estimated at ~13 us for the one CTA; keeping the counts in
+    // registers spilled 0.5 KB per thread.)
+    extern __shared__ __align__(16) unsigned char plan_smem[];
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(plan_smem); // [PER][kMsdPlanThreads] = 128 KB
     uint32_t sum = 0, mx = 0;
-#pragma unroll 8
-    for (int k = 0; k < PER; k++)
     {
-        const uint32_t c = __ldcg(hist + b0 + k);
-        sum += c;
-        mx = max(mx, c);
+        const uint4* h4 = reinterpret_cast<const uint4*>(hist + b0);
+#pragma unroll 4
+        for (int q = 0; q < PER / 4; q++)
+        {
+            const uint4 v = __ldcg(h4 + q);
+            sum += v.x + v.y + v.z + v.w;
+            mx = max(max(mx, v.x), max(max(v.y, v.z), v.w));
+            s_cnt[(4 * q + 0) * kMsdPlanThreads + tid] = (uint16_t)min(v.x, 0xffffu);
+            s_cnt[(4 * q + 1) * kMsdPlanThreads + tid] = (uint16_t)min(v.y, 0xffffu);
+            s_cnt[(4 * q + 2) * kMsdPlanThreads + tid] = (uint16_t)min(v.z, 0xffffu);
+            s_cnt[(4 * q + 3) * kMsdPlanThreads + tid] = (uint16_t)min(v.w, 0xffffu);
+        }
     }
+    auto count_of = [&](int k) { return (uint32_t)s_cnt[k * kMsdPlanThreads + tid]; }; // own entries only: no barrier needed
+
+    // ---- bin starts: exclusive prefix of the histogram ----
     uint32_t total = 0;
     const uint32_t seg_start = msd_block_scan<kMsdPlanThreads>(sum, s_warp, &total);
     const uint32_t block_max = __reduce_max_sync(0xffffffffu, mx);
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlan
 #pragma unroll 8
         for (int k = 0; k < PER; k++)
         {
-            const uint32_t c = __ldcg(hist + b0 + k);
+            const uint32_t c = count_of(k);
             if (c)
             {
                 ls = run;
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlan
 #pragma unroll 8
         for (int k = 0; k < PER; k++)
         {
-            const uint32_t c = __ldcg(hist + b0 + k);
+            const uint32_t c = count_of(k);
             if (c)
             {
                 const bool heavy = c > (uint32_t)(kMsdCap - kMsdWindow);
@@ -195,10 +211,11 @@ __global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlan
         uint32_t run = seg_start, next = first_range; // id of the next range to open
         bool hp = have_prev, ph = prev_heavy;
         uint32_t pw = prev_win;
+        uint32_t out2 = 0; // two 16-bit range ids per 32-bit store
 #pragma unroll 8
         for (int k = 0; k < PER; k++)
         {
-            const uint32_t c = __ldcg(hist + b0 + k);
+            const uint32_t c = count_of(k);
             uint32_t id = next ? next - 1 : 0; // empty bins: never looked up
             if (c)
             {
@@ -214,7 +231,11 @@ __global__ void __launch_bounds__(kMsdPlanThreads) msd_plan_kernel(const MsdPlan
                 ph = heavy;
                 pw = win;
             }
-            range_of_bin[b0 + k] = (uint16_t)min(id, (uint32_t)kMsdMaxRanges - 1u);
+            id = min(id, (uint32_t)kMsdMaxRanges - 1u);
+            if (k & 1)
+                reinterpret_cast<uint32_t*>(range_of_bin)[(b0 + k) >> 1] = out2 | (id << 16);
+            else
+                out2 = id;
             run += c;
         }
     }
@@ -667,10 +688,13 @@ __global__ void __launch_bounds__(kMsdThreads, 2) msd_sort_kernel(const MsdJobs 
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int g_msd_grid = 0;
+constexpr size_t kMsdPlanSmemBytes = (size_t)kMsdFineBins * sizeof(uint16_t); // the counts, 16 bits each
 
 cudaError_t msd_sort_configure()
 {
     cudaError_t e = cudaFuncSetAttribute(msd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(msd_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsdPlanSmemBytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0, dev = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msd_sort_kernel, kMsdThreads, sizeof(MsdSmem));
@@ -706,7 +730,7 @@ cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const 
         pj.ctl[i] = ctl[i];
         pj.T[i] = T[i];
     }
-    msd_plan_kernel<<<n, kMsdPlanThreads, 0, s>>>(pj);
+    msd_plan_kernel<<<n, kMsdPlanThreads, kMsdPlanSmemBytes, s>>>(pj);
     return cudaGetLastError();
 }
 
