@@ -378,7 +378,10 @@ def run_gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a collective that does not complete within three minutes aborts the job instead of hanging it
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
