@@ -160,6 +160,37 @@ int oibvh_scene_destroy(oibvh_scene* scene);
 int oibvh_scene_add_tree(oibvh_scene* scene, oibvh_tree* tree);
 /* restrict this scene to shard `rank` of `world` (seed BVTT nodes are dealt round-robin); default 0 of 1 */
 int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world);
+/* size the work queues up front (records): BVTT front (x2), candidate list, pair list. Queues otherwise start at
+ * 2^20 / 2^20 / 2^19 records and are regrown after an overflow; a multi-GPU scene cannot regrow (its pair list is
+ * mapped by the other ranks), so reserve before oibvh_mgpu_export. Synchronises; invalidates captured graphs. */
+int oibvh_scene_reserve(oibvh_scene* scene, uint32_t front_records, uint32_t candidate_records, uint32_t pair_records);
+
+/* ---- multi-GPU detection: the reference's DeviceType::GPU0..GPU8 + cudaSetDevice stub (include/cuda/scene.cuh:12-24,
+ *      src/cuda/scene.cu:229), redesigned: one scene per GPU over the SAME trees (every rank builds /
+ *      refits its own replica), oibvh_scene_set_shard(rank, world) deals the BVTT front of round 0 to the ranks, and
+ *      every rank's narrow phase appends its hits DIRECTLY to the gathering rank's pair list through a peer mapping
+ *      (NVLink): no collective and no host round trip per frame. Ranks may be threads of one process or one process
+ *      per GPU (CUDA IPC); the 160-byte handle is plain bytes the caller moves between them (MPI, a socket,
+ *      torch.distributed ...).
+ *        root:    oibvh_scene_reserve(..); oibvh_scene_set_shard(s, 0, W); oibvh_mgpu_export(s, &h);  -> send h
+ *        others:  oibvh_scene_set_shard(s, r, W); oibvh_mgpu_attach(s, &h);
+ *        frame:   every rank calls oibvh_scene_detect_async (or replays its graph) the SAME number of times. The
+ *                 root's detection completes only after every rank's hits of that frame have landed, so its
+ *                 get_counts / get_pairs / device_pairs return the gathered list; on the other ranks they report
+ *                 that rank's own counts and get_pairs fails (the list lives on the root).
+ *      A rank that never launches its frame makes the root's wait time out: OIBVH_ERR_INTERNAL from get_counts. */
+typedef struct oibvh_mgpu_handle
+{
+    unsigned char bytes[160];
+} oibvh_mgpu_handle;
+int oibvh_mgpu_export(oibvh_scene* root_scene, oibvh_mgpu_handle* out);
+int oibvh_mgpu_attach(oibvh_scene* scene, const oibvh_mgpu_handle* root);
+/* leave multi-GPU mode (unmaps the root's buffers); every rank, after the last frame has completed everywhere */
+int oibvh_mgpu_detach(oibvh_scene* scene);
+/* root only, optional: open the next frame (zero the counter block, let the other ranks append) ahead of the root's
+ * own detection -- lets a single device play several ranks one after the other (tests) */
+int oibvh_mgpu_open_frame(oibvh_scene* root_scene);
+
 /* Scene::detectCollision(GPUx, entryLevel, expandLevels) (src/cuda/scene.cu:157-185, 225-446): broad + narrow phase
  * over all object pairs i<j. entry_level / expand_levels keep the reference meaning (seed level; levels descended
  * per round); expand_levels = 0 lets the library choose the schedule (3 levels per round, round 0 absorbs the

@@ -85,6 +85,11 @@ _SIGNATURES = {
     "oibvh_scene_destroy": (C.c_int, [_vp]),
     "oibvh_scene_add_tree": (C.c_int, [_vp, _vp]),
     "oibvh_scene_set_shard": (C.c_int, [_vp, _u32, _u32]),
+    "oibvh_scene_reserve": (C.c_int, [_vp, _u32, _u32, _u32]),
+    "oibvh_mgpu_export": (C.c_int, [_vp, _vp]),
+    "oibvh_mgpu_attach": (C.c_int, [_vp, _vp]),
+    "oibvh_mgpu_detach": (C.c_int, [_vp]),
+    "oibvh_mgpu_open_frame": (C.c_int, [_vp]),
     "oibvh_scene_detect": (C.c_int, [_vp, _u32, _u32, _u32p, _u32p]),
     "oibvh_scene_detect_async": (C.c_int, [_vp, _u32, _u32]),
     "oibvh_scene_get_counts": (C.c_int, [_vp, _u32p, _u32p]),
@@ -629,6 +634,30 @@ class Scene:
 
     def detect_async(self, entryLevel=0, expandLevels=0):
         _check(_lib.oibvh_scene_detect_async(self._h, int(entryLevel), int(expandLevels)))
+
+    def reserve(self, front_records=0, candidate_records=0, pair_records=0):
+        """size the work queues up front (a multi-GPU scene cannot regrow them)"""
+        _check(_lib.oibvh_scene_reserve(self._h, int(front_records), int(candidate_records), int(pair_records)))
+
+    # -- multi-GPU: every rank appends its hits to rank 0's pair list through a peer mapping (oibvh_mgpu_*) --
+    MGPU_HANDLE_BYTES = 160
+
+    def mgpu_export(self):
+        """rank 0: returns the 160-byte handle the other ranks attach to (move it with any transport)"""
+        buf = C.create_string_buffer(self.MGPU_HANDLE_BYTES)
+        _check(_lib.oibvh_mgpu_export(self._h, C.cast(buf, _vp)))
+        return bytes(buf.raw)
+
+    def mgpu_attach(self, handle):
+        assert len(handle) == self.MGPU_HANDLE_BYTES
+        buf = C.create_string_buffer(bytes(handle), self.MGPU_HANDLE_BYTES)
+        _check(_lib.oibvh_mgpu_attach(self._h, C.cast(buf, _vp)))
+
+    def mgpu_detach(self):
+        _check(_lib.oibvh_mgpu_detach(self._h))
+
+    def mgpu_open_frame(self):
+        _check(_lib.oibvh_mgpu_open_frame(self._h))
 
     def counts(self):
         n, c = _u32(), _u32()

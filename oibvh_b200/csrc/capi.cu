@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 using namespace oibvh;
 
@@ -85,6 +86,9 @@ struct oibvh_ctx
     BatchTable small_table, xform_table;
     float* d_mats = nullptr;
     size_t d_mats_cap = 0;
+    // control blocks of the cooperative sort (kMaxLsdJobs jobs per launch). One set per context: the sorts of a
+    // context are ordered on `stream`, and every launch leaves the blocks re-armed.
+    uint32_t* lsd_ctl = nullptr;
 };
 
 struct oibvh_graph
@@ -110,10 +114,10 @@ struct oibvh_tree
     float* nodes = nullptr;        // N x 6
     // sort state: (keys_a, vals_a) hold the sorted keys / permutation after a build
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    uint2* sort_rec = nullptr; // 2 T (key, value) records: ping-pong buffers of the cooperative sort
     uint32_t* sort_ctl = nullptr; // [hist: passes*radix][ticket: passes (padded to 64)][status: passes*tiles*radix]
     size_t sort_ctl_words = 0;
     uint32_t* done_counter = nullptr;
-    uint32_t* msd_ctl = nullptr; // EXPERIMENTAL sort (OIBVH_SORT_MSD=1): allocated on first use
     // T <= kSmallTreeMax: built / refitted by one CTA (small_tree_kernel); no second sort buffers, no control blocks
     bool small = false;
     SmallTreeDesc* d_small = nullptr; // this tree's entry for single-tree launches
@@ -121,6 +125,7 @@ struct oibvh_tree
     cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
     bool consumed_recorded = false;
     bool upload_pending = false; // staging buffer holds positions that have not been packed yet
+    uint64_t epoch = 0;          // bumped by everything that changes what a detection would read (positions, nodes)
 };
 
 struct oibvh_scene
@@ -144,6 +149,18 @@ struct oibvh_scene
     uint32_t* h_counters = nullptr; // pinned host mirror
     uint32_t rank = 0, world = 1;
     uint32_t last_entry = 0, last_expand = 0, last_rounds = 0; // parameters of the last enqueued detection
+    // multi-GPU (oibvh_mgpu_*): protocol block of this scene + the gathering rank's buffers as seen from this device
+    uint32_t* mg_state = nullptr; // MG_WORDS, persistent (never zeroed per frame)
+    int mg_mode = 0;              // 0 = single GPU, 1 = gathering rank, 2 = remote rank
+    uint32_t* mg_root_state = nullptr;
+    uint32_t* mg_root_counters = nullptr;
+    uint4* mg_root_pairs = nullptr;
+    uint32_t mg_root_pair_cap = 0;
+    void *mg_ipc_block = nullptr, *mg_ipc_state = nullptr; // mappings opened with cudaIpcOpenMemHandle
+    bool mg_opened_ahead = false;
+    // the trees' modification counters when the last detection was enqueued (an overflow re-run is only valid if
+    // nothing has touched them since)
+    std::vector<uint64_t> enq_epochs;
 };
 
 namespace
@@ -211,9 +228,9 @@ void tree_free(oibvh_tree* t)
     cudaFree(t->keys_b);
     cudaFree(t->vals_a);
     cudaFree(t->vals_b);
+    cudaFree(t->sort_rec);
     cudaFree(t->d_small);
     cudaFree(t->sort_ctl);
-    cudaFree(t->msd_ctl);
     cudaFree(t->done_counter);
     if (t->ev_uploaded) cudaEventDestroy(t->ev_uploaded);
     if (t->ev_consumed) cudaEventDestroy(t->ev_consumed);
@@ -262,8 +279,8 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
     memcpy(t->mesh.v, mesh_aabb, sizeof(float) * 6);
     const uint32_t tiles = onesweep_tiles(T);
     const size_t radix = (size_t)1 << kRadixBits;
-    t->sort_ctl_words = std::max(kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix,
-                                 coop_sort_ctl_words());
+    // control block of the streaming sort (trees beyond the single-wave capacity): digit histograms, tickets, tile status
+    t->sort_ctl_words = T <= lsd_sort_capacity() ? 64 : kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix;
     t->small = T <= kSmallTreeMax;
     int rc = OIBVH_OK;
     // round the index buffers up to whole 16-byte groups so that 128-bit accesses of the last group stay in bounds
@@ -273,7 +290,9 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
         (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
         (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
         (t->small ? (rc = dev_alloc(&t->d_small, 1))
-                  : ((rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_b, T4)) ||
+                  : ((T <= lsd_sort_capacity()
+                          ? (rc = dev_alloc(&t->sort_rec, 2 * T4))                                       // single-wave sort
+                          : ((rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_b, T4)))) ||   // streaming sort
                      (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
                      (rc = dev_alloc(&t->done_counter, emit_counter_words(T))))))
     {
@@ -399,7 +418,9 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
         const long v = strtol(env, nullptr, 10);
         c->dense_seed_level = v <= 0 ? 1000u : (uint32_t)std::min<long>(std::max<long>(v, 6), 9);
     }
-    if (e == cudaSuccess) e = coop_sort_configure();
+    if (e == cudaSuccess) e = lsd_sort_configure();
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->lsd_ctl), sizeof(uint32_t) * kMaxLsdJobs * lsd_sort_ctl_words());
+    if (e == cudaSuccess) e = cudaMemset(c->lsd_ctl, 0, sizeof(uint32_t) * kMaxLsdJobs * lsd_sort_ctl_words());
     if (e == cudaSuccess) e = small_trees_configure();
     if (e != cudaSuccess)
     {
@@ -444,6 +465,7 @@ extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
     cudaFree(ctx->small_table.dev);
     cudaFree(ctx->xform_table.dev);
     cudaFree(ctx->d_mats);
+    cudaFree(ctx->lsd_ctl);
     delete ctx;
     return OIBVH_OK;
 }
@@ -703,8 +725,10 @@ extern "C" int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_posi
         CU(cudaMemcpyAsync(tree->pos_stage, host_positions, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(cudaEventRecord(tree->ev_uploaded, ctx->copy_stream));
         tree->upload_pending = true;
+        tree->epoch++;
         return OIBVH_OK;
     }
+    tree->epoch++;
     CU(launch_pack_positions(tree->pos_stage, tree->pos, tree->V, ctx->stream));
     count_launch(ctx);
     return OIBVH_OK;
@@ -715,6 +739,7 @@ extern "C" int oibvh_tree_set_positions_from_device(oibvh_tree* tree, const floa
     REQUIRE(tree && dev_positions, "NULL argument");
     DeviceGuard g(tree->ctx->device);
     tree->upload_pending = false; // superseded
+    tree->epoch++;
     CU(launch_pack_positions(dev_positions, tree->pos, tree->V, tree->ctx->stream));
     count_launch(tree->ctx);
     return OIBVH_OK;
@@ -730,60 +755,9 @@ extern "C" int oibvh_tree_transform(oibvh_tree* tree, const float M[16])
     }
     Mat4 m;
     memcpy(m.m, M, sizeof(float) * 16);
+    tree->epoch++;
     CU(launch_transform(tree->pos, tree->V, m, tree->ctx->stream));
     count_launch(tree->ctx);
-    return OIBVH_OK;
-}
-
-static bool msd_sort_requested()
-{
-    const char* e = getenv("OIBVH_SORT_MSD");
-    return e != nullptr && e[0] == '1';
-}
-
-// EXPERIMENTAL path (OIBVH_SORT_MSD=1): the keys of every tree are in keys_a. *sorted = true when the launches that
-// leave the result in (keys_a, vals_a) have been enqueued; false = use the 4-pass cooperative sort. Nothing is read
-// back (the plan's fallback is taken inside the kernel), so it is capturable -- the control blocks must then exist
-// already (one eager call first, like every *_many entry point).
-static int msd_sort_try(oibvh_tree* const* trees, uint32_t n, bool* sorted)
-{
-    *sorted = false;
-    oibvh_ctx* ctx = trees[0]->ctx;
-    static bool configured = false;
-    if (!configured)
-    {
-        if (ctx->capturing) return OIBVH_OK;
-        CU(msd_sort_configure());
-        configured = true;
-    }
-    if (n == 0 || n > 4) return OIBVH_OK;
-    uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
-    const uint32_t* kin[4];
-    for (uint32_t i = 0; i < n; i++) T[i] = trees[i]->T;
-    if (!msd_sort_fits(n, T)) return OIBVH_OK;
-    for (uint32_t i = 0; i < n; i++)
-    {
-        oibvh_tree* t = trees[i];
-        if (!t->msd_ctl)
-        {
-            if (ctx->capturing) return OIBVH_OK;
-            int rc = dev_alloc(&t->msd_ctl, msd_sort_ctl_words());
-            if (rc) return rc;
-        }
-        ka[i] = t->keys_a; kb[i] = t->keys_b; va[i] = t->vals_a; vb[i] = t->vals_b; ctl[i] = t->msd_ctl; T[i] = t->T;
-        kin[i] = t->keys_a;
-    }
-    CU(launch_msd_plan_many(n, kin, T, ctl, ctx->stream));
-    count_launch(ctx, n + 1);
-    cudaError_t e = launch_msd_sort_many(n, ka, kb, va, vb, T, ctl, ctx->stream);
-    if (e == cudaErrorInvalidValue)
-    {
-        cudaGetLastError();
-        return OIBVH_OK; // sizes do not fit the CTA ranges: 4-pass path
-    }
-    CU(e);
-    count_launch(ctx);
-    *sorted = true;
     return OIBVH_OK;
 }
 
@@ -804,31 +778,20 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
         CU(launch_small_trees(true, tree->d_small, tree->T <= kSmallBitonicSplit ? 1u : 0u, 1, s));
         count_launch(ctx);
         tree->built = true;
+        tree->epoch++;
         return OIBVH_OK;
     }
     const size_t radix = (size_t)1 << kRadixBits;
     uint32_t* hist = tree->sort_ctl;
     uint32_t* ticket = tree->sort_ctl + kRadixPasses * radix;
     uint32_t* status = ticket + 64;
-    if (tree->T <= coop_sort_capacity())
+    if (tree->sort_rec)
     {
-        // single-wave size: keys, then all radix passes in one cooperative launch
-        CU(cudaMemsetAsync(tree->sort_ctl, 0, 64 * sizeof(uint32_t), s));
+        // single-wave size: keys, then all radix passes in one cooperative launch (sort_lsd.cu)
         CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
         count_launch(ctx);
-        bool sorted = false;
-        if (msd_sort_requested())
-        {
-            // EXPERIMENTAL, opt-in (OIBVH_SORT_MSD=1): equal-count MSD partition + range-local sorts (sort_msd.cu)
-            oibvh_tree* one[1] = {tree};
-            int rc = msd_sort_try(one, 1, &sorted);
-            if (rc) return rc;
-        }
-        if (!sorted)
-        {
-            CU(launch_coop_sort(tree->keys_a, tree->keys_b, tree->vals_a, tree->vals_b, tree->T, tree->sort_ctl, s));
-            count_launch(ctx);
-        }
+        CU(launch_lsd_sort_many(1, &tree->keys_a, &tree->vals_a, &tree->sort_rec, &tree->T, ctx->lsd_ctl, s));
+        count_launch(ctx);
     }
     else
     {
@@ -855,6 +818,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
                         tree->done_counter, s));
     count_launch(ctx);
     tree->built = true;
+    tree->epoch++;
     return OIBVH_OK;
 }
 
@@ -934,7 +898,11 @@ extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
         StageScope scope(ctx, OIBVH_STAGE_BUILD);
         CU(launch_small_trees(true, table, n_bitonic, (uint32_t)small_list.size(), ctx->stream));
         count_launch(ctx, (n_bitonic ? 1 : 0) + (n_bitonic < small_list.size() ? 1 : 0));
-        for (auto* t : small_list) t->built = true;
+        for (auto* t : small_list)
+        {
+            t->built = true;
+            t->epoch++;
+        }
     }
     if (large_list.empty()) return OIBVH_OK;
     return build_large_many(large_list.data(), (uint32_t)large_list.size());
@@ -950,8 +918,10 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
         REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
         total += trees[i]->T;
     }
-    // every tree must still get enough CTAs for <= 16 keys per thread; the launcher re-checks and refuses otherwise
-    if (batch && total > coop_sort_capacity_multi()) batch = false;
+    // every tree must fit the single-wave sort and all of them together one launch; the launcher re-checks the split
+    if (batch && total > lsd_sort_capacity_multi()) batch = false;
+    for (uint32_t i = 0; i < n && batch; i++)
+        if (!trees[i]->sort_rec) batch = false;
     if (!batch)
     {
         for (uint32_t i = 0; i < n; i++)
@@ -969,46 +939,35 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     }
     StageScope scope(ctx, OIBVH_STAGE_BUILD);
     cudaStream_t s = ctx->stream;
-    uint32_t *ka[4], *kb[4], *va[4], *vb[4], *ctl[4], T[4];
-    // the key kernels of different trees are independent and latency-bound (random vertex gathers): odd trees go to
-    // the auxiliary stream like the emit kernels below
+    uint32_t *ka[4], *va[4], T[4];
+    uint2* rec[4];
+    // the key kernels of different trees are independent and gather-bound: odd trees go to the auxiliary stream like
+    // the emit kernels below
     CU(cudaEventRecord(ctx->ev_fork, s));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (uint32_t i = 0; i < n; i++)
     {
         oibvh_tree* t = trees[i];
         cudaStream_t st = (i & 1) ? ctx->aux_stream : s;
-        CU(cudaMemsetAsync(t->sort_ctl, 0, 64 * sizeof(uint32_t), st));
         CU(launch_morton_hist(t->faces_in, t->pos, t->T, t->mesh, t->keys_a, nullptr, st));
         count_launch(ctx);
-        ka[i] = t->keys_a; kb[i] = t->keys_b; va[i] = t->vals_a; vb[i] = t->vals_b; ctl[i] = t->sort_ctl; T[i] = t->T;
+        ka[i] = t->keys_a; va[i] = t->vals_a; rec[i] = t->sort_rec; T[i] = t->T;
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    bool msd_done = false;
-    if (msd_sort_requested())
+    const cudaError_t e = launch_lsd_sort_many(n, ka, va, rec, T, ctx->lsd_ctl, s);
+    if (e == cudaErrorInvalidValue)
     {
-        int rc = msd_sort_try(trees, n, &msd_done); // EXPERIMENTAL, opt-in (sort_msd.cu)
-        if (rc) return rc;
-    }
-    const cudaError_t e = msd_done ? cudaSuccess : launch_coop_sort_many(n, ka, kb, va, vb, T, ctl, s);
-    if (!msd_done && e == cudaErrorInvalidValue)
-    {
-        // very unequal sizes: sort one by one (keys are already computed)
+        // very unequal sizes (a tree would need more than kLsdKMulti keys per thread of its CTA share): sort one by one
         cudaGetLastError();
         for (uint32_t i = 0; i < n; i++)
         {
             oibvh_tree* t = trees[i];
-            if (t->T <= coop_sort_capacity())
-            {
-                CU(launch_coop_sort(t->keys_a, t->keys_b, t->vals_a, t->vals_b, t->T, t->sort_ctl, s));
-                count_launch(ctx);
-            }
-            else
-                return fail(OIBVH_ERR_INTERNAL, "build_many: tree %u does not fit the cooperative sort", i);
+            CU(launch_lsd_sort_many(1, &t->keys_a, &t->vals_a, &t->sort_rec, &t->T, ctx->lsd_ctl, s));
+            count_launch(ctx);
         }
     }
-    else if (!msd_done)
+    else
     {
         CU(e);
         count_launch(ctx);
@@ -1024,6 +983,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
                             (i & 1) ? ctx->aux_stream : s));
         count_launch(ctx);
         t->built = true;
+        t->epoch++;
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -1047,6 +1007,7 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
         CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
                             ctx->stream));
     count_launch(ctx);
+    tree->epoch++;
     return OIBVH_OK;
 }
 
@@ -1074,6 +1035,7 @@ extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
         StageScope scope(ctx, OIBVH_STAGE_REFIT);
         CU(launch_small_trees(false, table, n_bitonic, (uint32_t)small_list.size(), ctx->stream));
         count_launch(ctx);
+        for (auto* t : small_list) t->epoch++;
     }
     // the remaining trees one launch each; independent launches alternate between the two streams (see build_many)
     std::vector<oibvh_tree*> rest;
@@ -1105,6 +1067,7 @@ extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
         else
             CU(launch_tree_emit(false, nullptr, nullptr, t->faces, t->pos, t->nodes, t->T, t->done_counter, st));
         count_launch(ctx);
+        t->epoch++;
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -1170,6 +1133,7 @@ static int transform_many_impl(oibvh_tree* const* trees, uint32_t n, const float
     }
     CU(launch_transform_many(static_cast<const XformDesc*>(tab.dev), n, tab.total_blocks, d_mats, ctx->stream));
     count_launch(ctx);
+    for (uint32_t i = 0; i < n; i++) trees[i]->epoch++;
     return OIBVH_OK;
 }
 
@@ -1294,11 +1258,26 @@ extern "C" int oibvh_scene_create(oibvh_ctx* ctx, oibvh_scene** out)
     return OIBVH_OK;
 }
 
+static void mgpu_unmap(oibvh_scene* s)
+{
+    if (s->mg_ipc_block) cudaIpcCloseMemHandle(s->mg_ipc_block);
+    if (s->mg_ipc_state) cudaIpcCloseMemHandle(s->mg_ipc_state);
+    s->mg_ipc_block = s->mg_ipc_state = nullptr;
+    s->mg_root_state = s->mg_root_counters = nullptr;
+    s->mg_root_pairs = nullptr;
+    s->mg_root_pair_cap = 0;
+    s->mg_mode = 0;
+    s->mg_opened_ahead = false;
+}
+
 extern "C" int oibvh_scene_destroy(oibvh_scene* scene)
 {
     if (!scene) return OIBVH_OK;
     DeviceGuard g(scene->ctx->device);
     cudaStreamSynchronize(scene->ctx->stream);
+    scene->ctx->generation++; // graphs that captured this scene's buffers must not replay
+    mgpu_unmap(scene);
+    cudaFree(scene->mg_state);
     scene_free_buffers(scene);
     cudaFree(scene->d_objs);
     cudaFree(scene->counters_own);
@@ -1357,7 +1336,9 @@ static int scene_upload_objs(oibvh_scene* s)
     return OIBVH_OK;
 }
 
-static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_levels)
+// rerun = the overflow path of oibvh_scene_get_counts repeating the SAME detection with larger queues: it must read
+// exactly what the first attempt read, so it neither flushes pending uploads nor runs if a tree changed in between
+static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_levels, bool rerun = false)
 {
     const uint32_t requested_expand = expand_levels;
     oibvh_ctx* ctx = s->ctx;
@@ -1367,6 +1348,7 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     for (auto* t : s->trees)
     {
         maxL = std::max(maxL, t->L);
+        if (rerun) continue;
         int rc = tree_flush_upload(t); // the narrow phase reads the positions
         if (rc) return rc;
     }
@@ -1394,19 +1376,193 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     const uint32_t rounds = 1 + (maxL - reached + expand_levels - 1) / expand_levels; // leaf pairs leave as candidates
     if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
 
-    CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));
+    MgpuArgs mg{};
+    mg.mode = (uint32_t)s->mg_mode;
+    mg.world = s->world;
+    mg.state = s->mg_state;
+    mg.root_state = s->mg_root_state;
+    mg.root_counters = s->mg_root_counters;
+    mg.root_pairs = s->mg_root_pairs;
+    mg.root_pair_cap = s->mg_root_pair_cap;
+    if (s->mg_mode == 1)
+    {
+        // the gathering rank zeroes its counter block and THEN lets the other ranks append (MG_OPEN), in a launch of
+        // its own so that the opening never waits for this rank's machine-filling detection kernel
+        if (!s->mg_opened_ahead)
+        {
+            CU(launch_mgpu_open(s->counters, s->mg_state, st));
+            count_launch(ctx);
+        }
+        s->mg_opened_ahead = false;
+    }
+    else
+        CU(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * CTR_WORDS, st));
     {
         // broad and narrow phase run inside one persistent kernel; the stage clock covers both
         StageScope scope(ctx, OIBVH_STAGE_BROAD);
         CU(launch_collide(ctx->collide_grid, s->d_objs, n_obj, s->front[0], s->front[1], s->front_cap, s->cand,
                           s->cand_cap, s->pairs, s->pair_cap, s->counters, rounds, k0, expand_levels, s->rank,
-                          s->world, st));
+                          s->world, mg, st));
         count_launch(ctx);
     }
+    s->enq_epochs.resize(s->trees.size());
+    for (size_t i = 0; i < s->trees.size(); i++) s->enq_epochs[i] = s->trees[i]->epoch;
     CU(cudaMemcpyAsync(s->h_counters, s->counters, sizeof(uint32_t) * CTR_WORDS, cudaMemcpyDeviceToHost, st));
     s->last_entry = entry_level;
     s->last_expand = requested_expand;
     s->last_rounds = rounds;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_reserve(oibvh_scene* scene, uint32_t front_records, uint32_t candidate_records,
+                                   uint32_t pair_records)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    REQUIRE(scene->mg_mode == 0, "the queues of a multi-GPU scene are fixed (other ranks map them): detach first");
+    oibvh_ctx* ctx = scene->ctx;
+    REQUIRE(!ctx->capturing, "reserve outside a graph capture");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint32_t fc = std::max(std::max(front_records, scene->front_cap), 1u << 16);
+    const uint32_t cc = std::max(std::max(candidate_records, scene->cand_cap), 1u << 16);
+    const uint32_t pc = std::max(std::max(pair_records, scene->pair_cap), 1u << 16);
+    if (fc == scene->front_cap && cc == scene->cand_cap && pc == scene->pair_cap) return OIBVH_OK;
+    return scene_alloc_buffers(scene, fc, cc, pc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU: peer-mapped pair list of the gathering rank (see include/oibvh_b200.h)
+// ---------------------------------------------------------------------------------------------------
+namespace
+{
+struct MgpuHandleLayout
+{
+    cudaIpcMemHandle_t block; // [counters | pairs] allocation of the root
+    cudaIpcMemHandle_t state; // protocol block of the root
+    uint32_t pair_cap;
+    int32_t device;
+    uint64_t pid;             // same process: the raw pointers below are used instead of the IPC handles
+    uint64_t block_ptr, state_ptr;
+};
+static_assert(sizeof(MgpuHandleLayout) <= sizeof(oibvh_mgpu_handle), "handle layout must fit the public struct");
+
+int mgpu_state_alloc(oibvh_scene* s)
+{
+    if (!s->mg_state)
+    {
+        int rc = dev_alloc(&s->mg_state, (size_t)MG_WORDS);
+        if (rc) return rc;
+    }
+    CU(cudaMemsetAsync(s->mg_state, 0, sizeof(uint32_t) * MG_WORDS, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    return OIBVH_OK;
+}
+} // namespace
+
+extern "C" int oibvh_mgpu_export(oibvh_scene* scene, oibvh_mgpu_handle* out)
+{
+    REQUIRE(scene && out, "NULL argument");
+    REQUIRE(scene->rank == 0 && scene->world >= 2, "export from rank 0 of a world of >= 2 (oibvh_scene_set_shard first)");
+    oibvh_ctx* ctx = scene->ctx;
+    REQUIRE(!ctx->capturing, "export outside a graph capture");
+    DeviceGuard g(ctx->device);
+    if (scene->front_cap == 0)
+    {
+        int rc = scene_alloc_buffers(scene, 1u << 20, 1u << 20, 1u << 19);
+        if (rc) return rc;
+    }
+    int rc = mgpu_state_alloc(scene);
+    if (rc) return rc;
+    MgpuHandleLayout h;
+    memset(&h, 0, sizeof(h));
+    CU(cudaIpcGetMemHandle(&h.block, scene->pair_block));
+    CU(cudaIpcGetMemHandle(&h.state, scene->mg_state));
+    h.pair_cap = scene->pair_cap;
+    h.device = ctx->device;
+    h.pid = (uint64_t)getpid();
+    h.block_ptr = (uint64_t)(uintptr_t)scene->pair_block;
+    h.state_ptr = (uint64_t)(uintptr_t)scene->mg_state;
+    memset(out, 0, sizeof(*out));
+    memcpy(out->bytes, &h, sizeof(h));
+    scene->mg_mode = 1;
+    scene->mg_opened_ahead = false;
+    ctx->generation++; // graphs captured in single-GPU mode must be re-captured
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_mgpu_attach(oibvh_scene* scene, const oibvh_mgpu_handle* root)
+{
+    REQUIRE(scene && root, "NULL argument");
+    REQUIRE(scene->world >= 2 && scene->rank >= 1, "attach from a rank >= 1 (oibvh_scene_set_shard first)");
+    REQUIRE(scene->mg_mode == 0, "scene is already in multi-GPU mode");
+    oibvh_ctx* ctx = scene->ctx;
+    REQUIRE(!ctx->capturing, "attach outside a graph capture");
+    DeviceGuard g(ctx->device);
+    MgpuHandleLayout h;
+    memcpy(&h, root->bytes, sizeof(h));
+    int rc = mgpu_state_alloc(scene);
+    if (rc) return rc;
+    void *block = nullptr, *state = nullptr;
+    if (h.pid == (uint64_t)getpid())
+    {
+        // same process (one thread per GPU): the root's pointers are valid here once peer access is enabled
+        if (h.device != ctx->device)
+        {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+            if (!can) return fail(OIBVH_ERR_CUDA, "device %d cannot access device %d as a peer", ctx->device, h.device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError();
+            else
+                CU(e);
+        }
+        block = reinterpret_cast<void*>((uintptr_t)h.block_ptr);
+        state = reinterpret_cast<void*>((uintptr_t)h.state_ptr);
+    }
+    else
+    {
+        CU(cudaIpcOpenMemHandle(&block, h.block, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t e = cudaIpcOpenMemHandle(&state, h.state, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+        {
+            cudaIpcCloseMemHandle(block);
+            return fail(OIBVH_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        }
+        scene->mg_ipc_block = block;
+        scene->mg_ipc_state = state;
+    }
+    static_assert(CTR_WORDS * sizeof(uint32_t) % sizeof(uint4) == 0, "the counter block is a whole number of records");
+    scene->mg_root_counters = static_cast<uint32_t*>(block);
+    scene->mg_root_pairs = static_cast<uint4*>(block) + CTR_WORDS * sizeof(uint32_t) / sizeof(uint4);
+    scene->mg_root_state = static_cast<uint32_t*>(state);
+    scene->mg_root_pair_cap = h.pair_cap;
+    scene->mg_mode = 2;
+    ctx->generation++;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_mgpu_detach(oibvh_scene* scene)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    if (scene->mg_mode == 0) return OIBVH_OK;
+    DeviceGuard g(scene->ctx->device);
+    CU(cudaStreamSynchronize(scene->ctx->stream));
+    mgpu_unmap(scene);
+    scene->ctx->generation++;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_mgpu_open_frame(oibvh_scene* scene)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    REQUIRE(scene->mg_mode == 1, "only the gathering rank opens frames (oibvh_mgpu_export first)");
+    REQUIRE(!scene->mg_opened_ahead, "the next frame is already open");
+    oibvh_ctx* ctx = scene->ctx;
+    DeviceGuard g(ctx->device);
+    CU(launch_mgpu_open(scene->counters, scene->mg_state, ctx->stream));
+    count_launch(ctx);
+    scene->mg_opened_ahead = true;
     return OIBVH_OK;
 }
 
@@ -1454,6 +1610,12 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         uint32_t max_front = 0;
         for (uint32_t r = 0; r <= scene->last_rounds; r++) max_front = std::max(max_front, h[CTR_FRONT0 + r]);
         if (h[CTR_OVERFLOW] & 8u) return fail(OIBVH_ERR_INTERNAL, "grid barrier timed out in the detection kernel");
+        if (h[CTR_OVERFLOW] & 16u)
+            return fail(OIBVH_ERR_INTERNAL, "multi-GPU detection: a rank did not open / finish the frame in time");
+        if (h[CTR_OVERFLOW] != 0 && scene->mg_mode != 0)
+            return fail(OIBVH_ERR_OVERFLOW, "multi-GPU detection: a work queue overflowed (flags %u); the queues of a "
+                                            "multi-GPU scene are fixed -- oibvh_scene_reserve before oibvh_mgpu_export",
+                        h[CTR_OVERFLOW]);
         if (h[CTR_OVERFLOW] == 0)
         {
             if (n_pairs) *n_pairs = h[CTR_PAIRS];
@@ -1469,7 +1631,17 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
             return fail(OIBVH_ERR_OVERFLOW, "work queues cannot grow further");
         int rc = scene_alloc_buffers(scene, fc, cc, pc);
         if (rc) return rc;
-        rc = scene_enqueue(scene, scene->last_entry, scene->last_expand);
+        // Re-run only if the trees are exactly as the first attempt saw them. A caller that pipelines (detect_async,
+        // then uploads / transforms / refits for the next frame, then reads back) gets OIBVH_ERR_OVERFLOW instead of
+        // a pair set computed from a mixture of two frames; the queues are already regrown, so re-issuing the frame
+        // succeeds.
+        bool same = scene->enq_epochs.size() == scene->trees.size();
+        for (size_t i = 0; same && i < scene->trees.size(); i++)
+            same = scene->trees[i]->epoch == scene->enq_epochs[i] && !scene->trees[i]->upload_pending;
+        if (!same)
+            return fail(OIBVH_ERR_OVERFLOW, "a work queue overflowed and the trees have been modified since the "
+                                            "detection was enqueued: the queues have been regrown, re-issue the frame");
+        rc = scene_enqueue(scene, scene->last_entry, scene->last_expand, true);
         if (rc) return rc;
     }
     return fail(OIBVH_ERR_OVERFLOW, "work queues still overflow after repeated growth");
@@ -1486,6 +1658,7 @@ extern "C" int oibvh_scene_detect(oibvh_scene* scene, uint32_t entry_level, uint
 extern "C" int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs)
 {
     REQUIRE(scene != nullptr, "scene is NULL");
+    REQUIRE(scene->mg_mode != 2, "multi-GPU: the pair list is gathered on rank 0");
     uint32_t n = 0;
     int rc = oibvh_scene_get_counts(scene, &n, nullptr);
     if (rc) return rc;
@@ -1502,6 +1675,7 @@ extern "C" int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* hos
 extern "C" int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs)
 {
     REQUIRE(scene && dev_pairs && n_pairs, "NULL argument");
+    REQUIRE(scene->mg_mode != 2, "multi-GPU: the pair list is gathered on rank 0");
     int rc = oibvh_scene_get_counts(scene, n_pairs, nullptr);
     if (rc) return rc;
     *dev_pairs = reinterpret_cast<const oibvh_int_tri_pair*>(scene->pairs);

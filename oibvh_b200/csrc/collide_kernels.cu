@@ -544,8 +544,21 @@ __device__ __forceinline__ V3 load_v3(const float4* __restrict__ pos, uint32_t v
     return V3{p.x, p.y, p.z};
 }
 
+// system-scope accesses for the multi-GPU protocol words and the gathering rank's pair counter (peer memory)
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t r;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+// REMOTE = this rank is not the gathering rank: hits are appended to the ROOT's pair list through the peer mapping
+// (one system-scope atomic per warp claims the slots, then 16-byte stores over NVLink); the local counter still
+// counts this rank's own hits.
+template <bool REMOTE>
 __device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, const uint4* cand, uint32_t cand_cap,
-                             uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* counters, uint32_t n_cand)
+                             uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* counters, uint32_t n_cand,
+                             uint32_t* root_counters)
 {
     const uint32_t lane = lane_id();
     const uint32_t n = min(n_cand, cand_cap);
@@ -571,13 +584,24 @@ __device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ 
         if (mask)
         {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(counters + CTR_PAIRS, (uint32_t)__popc(mask));
+            if (lane == 0)
+            {
+                if (REMOTE)
+                {
+                    atomicAdd(counters + CTR_PAIRS, (uint32_t)__popc(mask)); // this rank's own count
+                    base = atomicAdd_system(root_counters + CTR_PAIRS, (uint32_t)__popc(mask));
+                }
+                else
+                    base = atomicAdd(counters + CTR_PAIRS, (uint32_t)__popc(mask));
+            }
             base = __shfl_sync(0xffffffffu, base, 0);
             if (hit)
             {
                 const uint32_t dst = base + __popc(mask & lanemask_lt());
                 if (dst < pair_cap)
                     pairs[dst] = c; // {bvhA, bvhB, triA, triB} == int_tri_pair_node_t
+                else if (REMOTE)
+                    atomicOr_system(root_counters + CTR_OVERFLOW, 4u);
                 else
                     atomicOr(counters + CTR_OVERFLOW, 4u);
             }
@@ -593,7 +617,7 @@ constexpr size_t kColSmemBytes = kColStageBytes;
 __global__ void __launch_bounds__(kColThreads, 1)
     collide_kernel(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* front0, uint4* front1, uint32_t front_cap,
                    uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap, uint32_t* counters,
-                   uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world)
+                   uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, const MgpuArgs mg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_stage = reinterpret_cast<uint4*>(smem_raw); // kColWarps x kStageCap records
@@ -606,6 +630,26 @@ __global__ void __launch_bounds__(kColThreads, 1)
         if (l == 0) s_objs[o] = d;
         s_lv[o * 64 + l] = l <= d.L ? level_offset(d.T, d.L, l) : 0u;
         s_lv[o * 64 + 32 + l] = l <= d.L ? level_count(d.T, d.L, l) : 0u;
+    }
+    // multi-GPU: this launch is frame MG_FRAME + 1 of the scene. A remote rank may append to the root's list only once
+    // the root has zeroed its counter block for this frame (MG_OPEN >= frame): one thread per CTA polls the root's word
+    // over NVLink NOW, off the critical path, and the narrow phase picks the answer up from shared memory.
+    __shared__ uint32_t s_mg_ok;
+    uint32_t mg_frame = 0;
+    if (mg.mode != 0)
+    {
+        mg_frame = __ldcg(mg.state + MG_FRAME) + 1; // updated only by the last CTA of the PREVIOUS launch
+        if (mg.mode == 2 && threadIdx.x == blockDim.x - 32)
+        {
+            uint32_t spins = 0, ok = 1;
+            while (ld_acquire_sys(mg.root_state + MG_OPEN) < mg_frame)
+                if (++spins > (1u << 22))
+                {
+                    ok = 0;
+                    break;
+                }
+            s_mg_ok = ok;
+        }
     }
     __syncthreads();
     uint32_t gen = 0;
@@ -649,10 +693,67 @@ __global__ void __launch_bounds__(kColThreads, 1)
     }
     const uint32_t n_cand = grid_barrier(counters, ++gen, counters + CTR_CANDIDATES);
     stamp(gen);
-    narrow_phase(s_objs, objs, cand, cand_cap, pairs, pair_cap, counters, n_cand);
+    if (mg.mode == 2)
+    {
+        if (s_mg_ok)
+            narrow_phase<true>(s_objs, objs, cand, cand_cap, mg.root_pairs, mg.root_pair_cap, counters, n_cand,
+                               mg.root_counters);
+        else if (threadIdx.x == 0)
+            atomicOr(counters + CTR_OVERFLOW, 16u); // the root never opened this frame
+    }
+    else
+        narrow_phase<false>(s_objs, objs, cand, cand_cap, pairs, pair_cap, counters, n_cand, nullptr);
     __syncthreads();
     stamp(gen + 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = n_stamps; // number of stamps
+    if (mg.mode != 0 && threadIdx.x == 0)
+    {
+        // Leave protocol: every CTA makes its appended pairs visible system-wide and counts itself out; the LAST one
+        // closes the frame -- a remote rank tells the root it is done, the root waits until every remote rank has
+        // said so, which makes "this kernel has completed on the root" mean "the gathered list is complete".
+        __threadfence_system();
+        if (atomicAdd(mg.state + MG_EXIT, 1u) == gridDim.x - 1)
+        {
+            __threadfence_system(); // acquire side of the other CTAs' fences
+            st_relaxed_gpu(mg.state + MG_EXIT, 0u);
+            st_relaxed_gpu(mg.state + MG_FRAME, mg_frame);
+            if (mg.mode == 2)
+                atomicAdd_system(mg.root_state + MG_DONE, 1u);
+            else
+            {
+                const uint32_t want = (mg.world - 1) * mg_frame;
+                uint32_t spins = 0;
+                while (ld_acquire_sys(mg.state + MG_DONE) < want)
+                    if (++spins > (1u << 24))
+                    {
+                        atomicOr(counters + CTR_OVERFLOW, 16u);
+                        atomicOr(mg.state + MG_FAIL, 1u);
+                        break;
+                    }
+            }
+        }
+    }
+}
+
+// root: zero the counter block of the coming frame, then publish MG_OPEN = frame at system scope. A separate
+// one-CTA launch so that the opening does not depend on the root's (cooperative, machine-filling) detection kernel
+// having started.
+__global__ void __launch_bounds__(CTR_WORDS) mgpu_open_kernel(uint32_t* counters, uint32_t* state)
+{
+    counters[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const uint32_t frame = __ldcg(state + MG_FRAME) + 1;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(state + MG_OPEN), "r"(frame) : "memory");
+    }
+}
+
+cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s)
+{
+    mgpu_open_kernel<<<1, CTR_WORDS, 0, s>>>(counters, state);
+    return cudaGetLastError();
 }
 
 // =================================================================================================
@@ -760,10 +861,11 @@ cudaError_t collide_configure(int* grid_blocks)
 cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
                            uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
                            uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
-                           uint32_t world, cudaStream_t s)
+                           uint32_t world, const MgpuArgs& mg, cudaStream_t s)
 {
+    MgpuArgs mga = mg;
     void* args[] = {&objs, &n_obj, &front0, &front1, &front_cap, &cand, &cand_cap, &pairs, &pair_cap,
-                    &counters, &rounds, &levels0, &levels, &rank, &world};
+                    &counters, &rounds, &levels0, &levels, &rank, &world, &mga};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(collide_kernel), dim3(grid_blocks),
                                        dim3(kColThreads), args, kColSmemBytes, s);
 }

@@ -197,7 +197,9 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         const uint32_t target = generation * participants;
         uint32_t spins = 0;
-        while (ld_acquire_gpu(counter) < target)
+        // relaxed polls (an acquire load invalidates the SM's L1 on EVERY iteration, under the feet of the CTA that
+        // shares the SM), one acquire fence once the count is reached
+        while (ld_relaxed_gpu(counter) < target)
         {
             if (++spins > (1u << 26))
             {
@@ -205,6 +207,7 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation
                 break;
             }
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }

@@ -15,7 +15,7 @@ struct Mat4
     float m[16]; // column-major like glm::mat4
 };
 
-// ---- radix sort configuration: 30-bit keys ----
+// ---- streaming radix sort (trees beyond the single-wave capacity): 30-bit keys, four 8-bit onesweep passes ----
 constexpr int kRadixBits = 8;
 constexpr int kRadixPasses = 4;
 constexpr int kSortItemsPerThread = 16;
@@ -32,30 +32,15 @@ uint32_t onesweep_tiles(uint32_t T);
 cudaError_t launch_onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                                  uint32_t* vals_out, uint32_t T, int pass, const uint32_t* hist, uint32_t* status,
                                  uint32_t* ticket, cudaStream_t s);
-// cooperative all-passes-in-one-launch sort for single-wave sizes (sort_coop.cu); result in (keys_a, vals_a).
-// ctl: coop_sort_ctl_words() words whose first 64 are zeroed before every launch.
-cudaError_t coop_sort_configure();
-uint32_t coop_sort_capacity(); // largest T the cooperative kernel takes on this device
-size_t coop_sort_ctl_words();
-uint32_t coop_sort_capacity_multi(); // total keys of a multi-array launch (longer per-CTA chunks)
-// n <= 4 arrays side by side in one launch (shared grid barriers); cudaErrorInvalidValue if they do not fit one wave.
-// The first 64 words of ctl[0] must be zero (barrier state); every ctl[i] holds that array's counts.
-cudaError_t launch_coop_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
-                                  uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s);
-cudaError_t launch_coop_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t T,
-                             uint32_t* ctl, cudaStream_t s);
-// EXPERIMENTAL (sort_msd.cu, off by default): one stable partition by equal-count key ranges + range-local sorts in
-// shared memory, with the 4-pass LSD sort built in as the fallback the plan can ask for. launch_msd_plan_many enqueues
-// histograms + plans into ctl[i] (msd_sort_ctl_words() words each); launch_msd_sort_many then sorts
-// (keys_a[i], identity) -> (keys_a[i], vals_a[i]) for n <= 4 arrays in one cooperative launch. Nothing is read back.
-cudaError_t msd_sort_configure();
-uint32_t msd_sort_capacity();
-bool msd_sort_fits(uint32_t n, const uint32_t* T); // do n arrays of these sizes fit one launch?
-size_t msd_sort_ctl_words();
-cudaError_t launch_msd_plan_many(uint32_t n, const uint32_t* const* keys, const uint32_t* T, uint32_t* const* ctl,
-                                 cudaStream_t s);
-cudaError_t launch_msd_sort_many(uint32_t n, uint32_t* const* keys_a, uint32_t* const* keys_b, uint32_t* const* vals_a,
-                                 uint32_t* const* vals_b, const uint32_t* T, uint32_t* const* ctl, cudaStream_t s);
+// Cooperative 3 x 10-bit LSD sort with ballot ranking (sort_lsd.cu): keys[i] sorted in place, permutation in vals[i];
+// rec[i] = 2 T[i] scratch records; ctl = kMaxLsdJobs blocks of lsd_sort_ctl_words() words, zeroed once.
+constexpr int kMaxLsdJobs = 4;
+cudaError_t lsd_sort_configure();
+uint32_t lsd_sort_capacity();
+uint32_t lsd_sort_capacity_multi();
+size_t lsd_sort_ctl_words();
+cudaError_t launch_lsd_sort_many(uint32_t n, uint32_t* const* keys, uint32_t* const* vals, uint2* const* rec,
+                                 const uint32_t* T, uint32_t* ctl, cudaStream_t s);
 cudaError_t tree_emit_configure();
 // arrival counters of the hierarchical top-of-tree completion (zeroed once; the kernel re-arms them)
 size_t emit_counter_words(uint32_t T);
@@ -117,13 +102,38 @@ enum
 {
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
-    CTR_OVERFLOW = 2, // bit 0: front, bit 1: candidates, bit 2: pairs, bit 3: grid barrier timed out
+    CTR_OVERFLOW = 2, // bit 0: front, bit 1: candidates, bit 2: pairs, bit 3: grid barrier timed out, bit 4: multi-GPU wait timed out
     CTR_BARRIER = 3,  // arrival counter of the grid barrier
     CTR_FRONT0 = 8,   // CTR_FRONT0 + r = size of the front consumed by round r
     CTR_MAX_ROUNDS = 48,
     CTR_TIME0 = 64,   // CTR_TIME0 + i = SM cycle counter (low 32 bits) of CTA 0 at phase boundary i
     CTR_WORDS = 128
 };
+
+// ---- multi-GPU detection: replicated BVH, round 0 dealt to `world` ranks, and every rank's narrow phase
+// appends its hits DIRECTLY to the gathering rank's pair list through a peer mapping (NVLink), so a frame needs no
+// collective. Protocol words live in a small persistent block per scene (never zeroed per frame):
+enum
+{
+    MG_FRAME = 0,  // detections completed on this scene since attach (written by the last CTA to leave)
+    MG_OPEN = 1,   // root only: last frame whose counter block has been zeroed (remote ranks poll it before appending)
+    MG_DONE = 2,   // root only: remote completions so far (monotonic: every remote rank adds 1 per frame)
+    MG_EXIT = 3,   // CTAs that have left the current launch (the last one re-arms it)
+    MG_FAIL = 4,   // sticky: a wait timed out
+    MG_WORDS = 64
+};
+struct MgpuArgs
+{
+    uint32_t mode;          // 0 = single GPU, 1 = gathering rank (root), 2 = remote rank
+    uint32_t world;
+    uint32_t* state;        // this scene's protocol block
+    uint32_t* root_state;   // remote: the root's protocol block (peer mapping)
+    uint32_t* root_counters; // remote: the root's counter block
+    uint4* root_pairs;      // remote: the root's pair list
+    uint32_t root_pair_cap;
+};
+// root: zero the counter block of the coming frame, then publish MG_OPEN = frame (system scope)
+cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s);
 
 // Whole detection in one cooperative launch: seeds (one root pair per object pair i<j) -> `rounds` expansion
 // rounds (round 0 descends levels0 levels, the others `levels`; rank/world shard the children of round 0) ->
@@ -132,7 +142,7 @@ cudaError_t collide_configure(int* grid_blocks);
 cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
                            uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
                            uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
-                           uint32_t world, cudaStream_t s);
+                           uint32_t world, const MgpuArgs& mg, cudaStream_t s);
 
 // collided-triangle vertex stream (Scene::convertToVertexArray) and node-box wireframes
 // (OibvhTree::convertToVertexArray) as device-side gathers

@@ -1,9 +1,11 @@
-"""Multi-GPU plumbing: one process per GPU, the BVH replicated, the BVTT seed front sharded
-(oibvh_scene_set_shard), and only the pair list exchanged.
+"""Multi-GPU plumbing: one process per GPU, the BVH replicated, the BVTT front of round 0 dealt to the ranks
+(oibvh_scene_set_shard), and only the pair list gathered.
 
-`torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests) carries the single exchange step of the
-path: an all-gather of the per-rank pair counts followed by an all-gather of the 16-byte pair records padded
-to the largest shard. Messages are KB-MB, i.e. latency-bound; nothing else crosses GPUs.
+The data path needs NO collective per frame: every rank's narrow phase appends its hits directly to rank 0's pair list
+through a CUDA-IPC peer mapping over NVLink (C ABI: oibvh_mgpu_export / oibvh_mgpu_attach; protocol in
+csrc/collide_kernels.cu). `torch.distributed` is only the transport of the 160-byte handle at set-up (`attach`) and
+the barrier around timed regions. `gather_pairs` is the collective alternative (all-gather of counts, then of the
+padded 16-byte records; NCCL over NVLink on GPUs, gloo in the CPU tests), kept as the cross-check of the peer path.
 """
 import torch
 import torch.distributed as dist
@@ -27,6 +29,25 @@ def gather_pairs(local_pairs, n_local, group=None):
     return torch.cat([recv[r][:counts[r]] for r in range(world)], dim=0)
 
 
+def attach(scene, rank, world, group=None, src=0):
+    """Put `scene` (one per rank, same trees on every rank) into multi-GPU mode: rank `src` exports the handle of its
+    pair list, the handle travels by broadcast, the others map it. Collective: every rank of the group calls it."""
+    scene.set_shard(rank, world)
+    box = [scene.mgpu_export() if rank == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    if rank != src:
+        scene.mgpu_attach(box[0])
+    dist.barrier(group=group)
+
+
+def detach(scene, group=None):
+    """leave multi-GPU mode after the last frame has completed on every rank"""
+    scene.ctx.synchronize()
+    dist.barrier(group=group)
+    scene.mgpu_detach()
+    dist.barrier(group=group)
+
+
 def pairs_tensor_from_device_ptr(ptr, n, device):
     """zero-copy int32 [n,4] view of the scene's device pair list (oibvh_scene_device_pairs)"""
     if n == 0:
@@ -39,40 +60,3 @@ def pairs_tensor_from_device_ptr(ptr, n, device):
     h.__cuda_array_interface__ = {"shape": (int(n), 4), "typestr": "<i4", "data": (int(ptr), False), "version": 3,
                                   "strides": None}
     return torch.as_tensor(h, device=device)
-
-
-# ---- fixed-size exchange: ONE collective per frame -----------------------------------------------------------------
-# A scene's 512-byte counter block is the head of its pair-list allocation (include/oibvh_b200.h,
-# oibvh_scene_device_counters), so [counter block | first `cap` pair records] is one contiguous device range.
-HEAD_RECORDS = 32  # 512 bytes / 16-byte records; row 0 = (candidates, pairs, overflow flags, barrier word)
-
-
-def block_view(counters_ptr, cap, device):
-    """zero-copy int32 [HEAD_RECORDS + cap, 4] view of a scene's [counter block | pair list] device range"""
-    return pairs_tensor_from_device_ptr(counters_ptr, HEAD_RECORDS + int(cap), device)
-
-
-def gather_blocks(out, block, group=None):
-    """all-gather every rank's block into out ([world * (HEAD_RECORDS + cap), 4]); enqueue-only on NCCL"""
-    dist.all_gather_into_tensor(out, block, group=group)
-
-
-def unpack_blocks(gathered, world, cap):
-    """-> (per-rank pair counts, list of per-rank [min(count, cap), 4] views, truncated?) from a gathered buffer"""
-    v = gathered.view(world, HEAD_RECORDS + int(cap), 4)
-    counts = [int(c) for c in v[:, 0, 1].tolist()]
-    parts = [v[r, HEAD_RECORDS:HEAD_RECORDS + min(counts[r], int(cap))] for r in range(world)]
-    return counts, parts, max(counts) > int(cap)
-
-
-def agree_capacity(n_local, floor=4096, ceiling=None, device=None, group=None):
-    """Fixed per-rank record count of the block exchange, IDENTICAL on every rank (a collective with different sizes
-    per rank never completes): 4x the LARGEST per-rank pair count (all-reduce MAX), rounded up to a power of two,
-    at least `floor`, at most `ceiling` (the smallest pair-list capacity, also agreed by all-reduce MIN)."""
-    t = torch.tensor([int(n_local), -int(ceiling) if ceiling is not None else -(1 << 62)], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    n_max, ceil_min = int(t[0].item()), -int(t[1].item())
-    cap = int(floor)
-    while cap < 4 * n_max:
-        cap *= 2
-    return min(cap, ceil_min)

@@ -225,41 +225,51 @@ def test_many_small_trees_in_one_launch(ctx, port):
         assert_bit_equal(t.download()["nodes"], w2["nodes"], "rebuild after the transform")
 
 
-@pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("OIBVH_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental MSD sort (sort_msd.cu): set OIBVH_TEST_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("T", [5000, 65536, 200000, 1048576])
-def test_experimental_msd_sort_builds_the_same_tree(ctx, port, T):
-    """OIBVH_SORT_MSD=1: equal-count MSD partition + range-local sorts must give the 4-pass sort's permutation"""
+def test_single_wave_sort_builds_the_same_tree(ctx, port, T):
+    """the cooperative 3 x 10-bit sort (sort_lsd.cu): one tree over the whole grid, two trees side by side in one
+    launch (oibvh_tree_build_many), eagerly and replayed from a graph (the kernel re-arms its control block)"""
     nu = max(16, int((T / 2) ** 0.5) + 2)
     pos, faces = meshgen.blob(nu, nu, seed=7)
     faces = meshgen.shuffle_faces(faces)[:T]
     want = port.build(pos, faces, port.mesh_aabb(pos))
-    os.environ["OIBVH_SORT_MSD"] = "1"
-    try:
-        t = ob.OibvhTree(ob.Mesh(pos, faces), ctx=ctx)
+    t = ob.OibvhTree(ob.Mesh(pos, faces), ctx=ctx)
+    for _ in range(2):  # twice: the second launch starts from the control block the first one left behind
         t.build()
         got = t.download()
-    finally:
-        os.environ.pop("OIBVH_SORT_MSD", None)
-    assert np.array_equal(got["perm"], want["perm"])
-    assert np.array_equal(got["nodes"].view(np.uint32), want["nodes"].view(np.uint32))
-    # two trees side by side in one launch (oibvh_tree_build_many), eagerly and replayed from a graph
-    os.environ["OIBVH_SORT_MSD"] = "1"
-    try:
-        t2 = ob.OibvhTree(ob.Mesh(pos, faces[::-1].copy()), ctx=ctx)
-        want2 = port.build(pos, faces[::-1].copy(), port.mesh_aabb(pos))
-        ob.build_many([t, t2])
-        ctx.capture_begin()
-        ob.build_many([t, t2])
-        g = ctx.capture_end()
+        assert np.array_equal(t.sorted_keys(), want["keys"])
+        assert np.array_equal(got["perm"], want["perm"])
+        assert_bit_equal(got["nodes"], want["nodes"], "nodes")
+    faces2 = np.ascontiguousarray(faces[::-1][: max(2, (2 * T) // 3)])
+    t2 = ob.OibvhTree(ob.Mesh(pos, faces2), ctx=ctx)
+    want2 = port.build(pos, faces2, port.mesh_aabb(pos))
+    ob.build_many([t, t2])
+    ctx.capture_begin()
+    ob.build_many([t, t2])
+    g = ctx.capture_end()
+    for _ in range(3):
         g.launch()
-        ctx.synchronize()
-        a, b = t.download(), t2.download()
-        g.close()
-    finally:
-        os.environ.pop("OIBVH_SORT_MSD", None)
+    ctx.synchronize()
+    a, b = t.download(), t2.download()
+    g.close()
     assert np.array_equal(a["perm"], want["perm"]) and np.array_equal(b["perm"], want2["perm"])
-    assert np.array_equal(b["nodes"].view(np.uint32), want2["nodes"].view(np.uint32))
+    assert_bit_equal(a["nodes"], want["nodes"], "build_many nodes A")
+    assert_bit_equal(b["nodes"], want2["nodes"], "build_many nodes B")
     t.close()
     t2.close()
+
+
+def test_sort_heavy_ties_pole_mesh_and_all_equal_keys(ctx, port):
+    """key distributions that break bucket-based sorts: the poles of a UV sphere put thousands of triangles into one
+    Morton cell, and a mesh box far larger than the mesh collapses EVERY key to one value (the order is then the
+    input order: stability is all that is left)"""
+    pos, faces = port.gen_uv_sphere(384)  # 294 912 triangles, 768 zero-area triangles at the poles
+    faces = meshgen.shuffle_faces(faces, seed=5)
+    check_build(ctx, port, pos, faces)
+    coarse = np.array([-32, -32, -32, 32, 32, 32], np.float32)  # a few thousand occupied cells, thousands of ties each
+    tree, _, _ = check_build(ctx, port, pos, faces, coarse)
+    assert np.bincount(np.unique(tree.sorted_keys(), return_inverse=True)[1]).max() > 500
+    aabb = np.array([1e6, 1e6, 1e6, 3e6, 3e6, 3e6], np.float32)  # every centroid quantises to cell 0
+    tree, mesh, want = check_build(ctx, port, pos, faces, aabb)
+    assert len(np.unique(tree.sorted_keys())) == 1
+    assert np.array_equal(tree.download()["perm"], np.arange(len(faces), dtype=np.uint32))

@@ -100,84 +100,60 @@ def test_gather_pairs_world2_gloo():
         assert np.array_equal(out[r], want)
 
 
-def _block_worker(rank, world, port_no, q):
-    import torch
+class _FakeScene:
+    """records what distributed.attach / detach do to a scene (the real calls need a GPU)"""
+
+    class _Ctx:
+        def synchronize(self):
+            pass
+
+    def __init__(self, rank):
+        self.rank_id, self.calls, self.ctx = rank, [], self._Ctx()
+
+    def set_shard(self, rank, world):
+        self.calls.append(("set_shard", rank, world))
+
+    def mgpu_export(self):
+        self.calls.append(("export",))
+        return bytes(range(160))
+
+    def mgpu_attach(self, handle):
+        self.calls.append(("attach", bytes(handle)))
+
+    def mgpu_detach(self):
+        self.calls.append(("detach",))
+
+
+def _attach_worker(rank, world, port_no, q):
     import torch.distributed as dist
     from oibvh_b200 import distributed as obd
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        cap = 8
-        # what a scene's device range looks like: 32-record counter block (row 0 = cand, pairs, flags, -) + pair list
-        n = [3, 11][rank]  # rank 1 overflows the fixed exchange
-        block = torch.full((obd.HEAD_RECORDS + cap, 4), -7, dtype=torch.int32)
-        block[0] = torch.tensor([5 * n, n, 0, 0], dtype=torch.int32)
-        m = min(n, cap)
-        block[obd.HEAD_RECORDS:obd.HEAD_RECORDS + m] = torch.arange(m * 4, dtype=torch.int32).reshape(m, 4) + 1000 * rank
-        out = torch.empty((world * (obd.HEAD_RECORDS + cap), 4), dtype=torch.int32)
-        obd.gather_blocks(out, block)
-        counts, parts, truncated = obd.unpack_blocks(out, world, cap)
-        q.put((rank, counts, [p.numpy().copy() for p in parts], truncated))
+        sc = _FakeScene(rank)
+        obd.attach(sc, rank, world)
+        obd.detach(sc)
+        q.put((rank, sc.calls))
     finally:
         dist.destroy_process_group()
 
 
-def test_single_collective_block_exchange_world2_gloo():
-    """[counter block | pair list] of every rank in ONE all-gather (the multi-GPU frame's only exchange)"""
+@pytest.mark.parametrize("world", [2, 3])
+def test_mgpu_handle_transport_gloo(world):
+    """set-up of the peer-mapped pair list: rank 0 exports, the 160-byte handle travels by broadcast, every other rank
+    attaches exactly those bytes; nothing else is exchanged (the frames themselves need no collective)"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
-    procs = [ctx.Process(target=_block_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    procs = [ctx.Process(target=_attach_worker, args=(r, world, port_no, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    res = dict(q.get(timeout=180) for _ in range(world))
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, counts, parts, truncated in res:
-        assert counts == [3, 11] and truncated  # rank 1 holds 11 > cap = 8 records: reported, never silently dropped
-        assert np.array_equal(parts[0], np.arange(12).reshape(3, 4))
-        assert np.array_equal(parts[1], np.arange(32).reshape(8, 4) + 1000)
-
-
-def _cap_worker(rank, world, port_no, q):
-    import torch
-    import torch.distributed as dist
-    from oibvh_b200 import distributed as obd
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port_no)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        n_local = [700, 1100, 90][rank]          # 4x -> 2800 / 4400 / 360: a rank-local rule would give 4096 / 8192 / 4096
-        ceiling = [1 << 19, 1 << 19, 1 << 20][rank]
-        cap = obd.agree_capacity(n_local, floor=4096, ceiling=ceiling)
-        cap_small = obd.agree_capacity(n_local, floor=4096, ceiling=[6000, 5000, 7000][rank])
-        # the exchange itself with the agreed size, world = 3
-        block = torch.full((obd.HEAD_RECORDS + cap, 4), rank, dtype=torch.int32)
-        block[0] = torch.tensor([0, n_local, 0, 0], dtype=torch.int32)
-        out = torch.empty((world * (obd.HEAD_RECORDS + cap), 4), dtype=torch.int32)
-        obd.gather_blocks(out, block)
-        counts, parts, truncated = obd.unpack_blocks(out, world, cap)
-        q.put((rank, cap, cap_small, counts, [int(p[0, 0]) for p in parts], truncated))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_exchange_capacity_is_agreed_across_ranks_world3_gloo():
-    """regression: the fixed exchange size must not depend on the rank's own pair count (it hung at 4 GPUs)"""
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port_no = _free_port()
-    procs = [ctx.Process(target=_cap_worker, args=(r, 3, port_no, q)) for r in range(3)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=180) for _ in range(3)]
-    for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
-    for rank, cap, cap_small, counts, firsts, truncated in res:
-        assert cap == 8192 and cap_small == 5000          # MAX of the counts, MIN of the ceilings: same on every rank
-        assert counts == [700, 1100, 90] and firsts == [0, 1, 2] and not truncated
+    assert res[0] == [("set_shard", 0, world), ("export",), ("detach",)]
+    for r in range(1, world):
+        assert res[r] == [("set_shard", r, world), ("attach", bytes(range(160))), ("detach",)]
