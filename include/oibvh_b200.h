@@ -67,7 +67,12 @@ enum
     OIBVH_STAGE_REFIT = 1,
     OIBVH_STAGE_BROAD = 2,
     OIBVH_STAGE_NARROW = 3,
-    OIBVH_STAGE_COUNT = 4
+    /* kernels inside the stages above (the per-kernel roofline table of bench.py): */
+    OIBVH_STAGE_KEYS = 4,      /* build: Morton keys */
+    OIBVH_STAGE_SORT = 5,      /* build: stable radix sort of (key, face id) */
+    OIBVH_STAGE_EMIT = 6,      /* build: face gather + leaf boxes + bottom-up reduction */
+    OIBVH_STAGE_TRANSFORM = 7, /* oibvh_tree_transform[_many] */
+    OIBVH_STAGE_COUNT = 8
 };
 
 const char* oibvh_last_error(void);

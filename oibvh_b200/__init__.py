@@ -22,6 +22,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OIBVH_B200_LIB") or os.path.join(_HERE, "liboibvh_b200.so")
 
 STAGES = ("build", "refit", "broad", "narrow")
+# kernels inside the stages (oibvh_ctx_stage_ms also reports them): keys + sort + emit = build
+SUBSTAGES = ("keys", "sort", "emit", "transform")
 
 
 class OibvhError(RuntimeError):
@@ -223,9 +225,9 @@ class Context:
         _check(_lib.oibvh_ctx_enable_timing(self._h, 1 if on else 0))
 
     def stage_ms(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 8)()
         _check(_lib.oibvh_ctx_stage_ms(self._h, ms))
-        return dict(zip(STAGES, [float(x) for x in ms]))
+        return dict(zip(STAGES + SUBSTAGES, [float(x) for x in ms]))
 
     def capture_begin(self):
         _check(_lib.oibvh_ctx_capture_begin(self._h))

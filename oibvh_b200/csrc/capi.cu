@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -73,7 +74,7 @@ struct oibvh_ctx
     uint32_t dense_seed_level = 8; // two-body scenes: level tested densely in round 0 (OIBVH_DENSE_SEED_LEVEL, 0 = off)
     uint64_t generation = 0; // bumped whenever device buffers referenced by enqueued work are reallocated
     std::vector<StageEvent> events;
-    float stage_ms[OIBVH_STAGE_COUNT] = {0, 0, 0, 0};
+    float stage_ms[OIBVH_STAGE_COUNT] = {};
     // device tables of the *_many entry points, kept while the same list of trees is passed again (per-frame calls
     // then upload nothing and can be captured into a graph)
     struct BatchTable
@@ -756,6 +757,7 @@ extern "C" int oibvh_tree_transform(oibvh_tree* tree, const float M[16])
     Mat4 m;
     memcpy(m.m, M, sizeof(float) * 16);
     tree->epoch++;
+    StageScope st(tree->ctx, OIBVH_STAGE_TRANSFORM);
     CU(launch_transform(tree->pos, tree->V, m, tree->ctx->stream));
     count_launch(tree->ctx);
     return OIBVH_OK;
@@ -788,17 +790,25 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     if (tree->sort_rec)
     {
         // single-wave size: keys, then all radix passes in one cooperative launch (sort_lsd.cu)
-        CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
-        count_launch(ctx);
+        {
+            StageScope sk(ctx, OIBVH_STAGE_KEYS);
+            CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, nullptr, s));
+            count_launch(ctx);
+        }
+        StageScope ss(ctx, OIBVH_STAGE_SORT);
         CU(launch_lsd_sort_many(1, &tree->keys_a, &tree->vals_a, &tree->sort_rec, &tree->T, ctx->lsd_ctl, s));
         count_launch(ctx);
     }
     else
     {
         // streaming size: keys + digit histograms, then one onesweep launch per digit
-        CU(cudaMemsetAsync(tree->sort_ctl, 0, tree->sort_ctl_words * sizeof(uint32_t), s));
-        CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, hist, s));
-        count_launch(ctx);
+        {
+            StageScope sk(ctx, OIBVH_STAGE_KEYS);
+            CU(cudaMemsetAsync(tree->sort_ctl, 0, tree->sort_ctl_words * sizeof(uint32_t), s));
+            CU(launch_morton_hist(tree->faces_in, tree->pos, tree->T, tree->mesh, tree->keys_a, hist, s));
+            count_launch(ctx);
+        }
+        StageScope ss(ctx, OIBVH_STAGE_SORT);
         uint32_t *kin = tree->keys_a, *kout = tree->keys_b, *vin = nullptr, *vout = tree->vals_b;
         for (int p = 0; p < kRadixPasses; p++)
         {
@@ -814,6 +824,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
         }
     }
     static_assert(kRadixPasses % 2 == 0, "an even number of passes leaves the result in (keys_a, vals_a)");
+    StageScope se(ctx, OIBVH_STAGE_EMIT);
     CU(launch_tree_emit(true, tree->faces_in, tree->vals_a, tree->faces, tree->pos, tree->nodes, tree->T,
                         tree->done_counter, s));
     count_launch(ctx);
@@ -943,6 +954,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     uint2* rec[4];
     // the key kernels of different trees are independent and gather-bound: odd trees go to the auxiliary stream like
     // the emit kernels below
+    std::unique_ptr<StageScope> sub(new StageScope(ctx, OIBVH_STAGE_KEYS)); // per-kernel clocks inside the stage
     CU(cudaEventRecord(ctx->ev_fork, s));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (uint32_t i = 0; i < n; i++)
@@ -955,6 +967,8 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    sub.reset(); // records the end of the key kernels before the next scope opens
+    sub.reset(new StageScope(ctx, OIBVH_STAGE_SORT));
     const cudaError_t e = launch_lsd_sort_many(n, ka, va, rec, T, ctx->lsd_ctl, s);
     if (e == cudaErrorInvalidValue)
     {
@@ -974,6 +988,8 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     }
     // the emit kernels are independent: odd trees go to the auxiliary stream, so the kernels share the machine and
     // the wave quantisation of each (1024 CTAs on 444 slots = 2.3 -> 3 waves) is paid once for all of them
+    sub.reset();
+    sub.reset(new StageScope(ctx, OIBVH_STAGE_EMIT));
     CU(cudaEventRecord(ctx->ev_fork, s));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (uint32_t i = 0; i < n; i++)
@@ -1131,6 +1147,7 @@ static int transform_many_impl(oibvh_tree* const* trees, uint32_t n, const float
         CU(cudaMemcpyAsync(ctx->d_mats, mats, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_mats = ctx->d_mats;
     }
+    StageScope st(ctx, OIBVH_STAGE_TRANSFORM);
     CU(launch_transform_many(static_cast<const XformDesc*>(tab.dev), n, tab.total_blocks, d_mats, ctx->stream));
     count_launch(ctx);
     for (uint32_t i = 0; i < n; i++) trees[i]->epoch++;

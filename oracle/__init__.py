@@ -16,6 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_PATH = os.path.join(_HERE, "liboibvh_oracle.so")
 REF_PATH = os.path.join(_HERE, "_ref", "liboibvh_ref.so")
+# the reference CPU classes with `int a[19]` -> `int a[64]` (oracle/Makefile target refdeep): timing arm of bench.py only
+REF_DEEP_PATH = os.path.join(_HERE, "_ref", "liboibvh_ref_deep.so")
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)
@@ -213,6 +215,10 @@ class Port:
 # =====================================================================================================
 def ref_available():
     return os.path.exists(REF_PATH)
+
+
+def ref_deep_available():
+    return os.path.exists(REF_DEEP_PATH)
 
 
 class Ref:

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.gpu
 def test_bench_line_has_the_contract_keys(ctx):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "12", "--warmup", "3",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--no-cpu-baseline", "--configs", "0,3", "--bodies", "96"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, res.stdout[-2000:]
@@ -35,6 +36,16 @@ def test_bench_line_has_the_contract_keys(ctx):
     c = d["clocks"]
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(c)
     assert d["pairs"] > 0 and d["candidates"] >= d["pairs"]
+    # per-kernel roofline table: every frame kernel with its SURVEY.md bytes, its time and its share; `roofline` names
+    # the one with the largest share
+    k = d["kernels"]
+    assert len(k) == 6 and abs(sum(v["share_of_frame"] for v in k.values()) - 1.0) < 1e-6
+    assert r["kernel"].startswith(max(k, key=lambda n: k[n]["ms"]))
+    # one sub-record per requested BASELINE.json config (configs[1] is the line itself)
+    recs = {c["config"]: c for c in d["configs"]}
+    assert set(recs) == {"configs[0]", "configs[3]"}
+    for c in recs.values():
+        assert c["ms_per_frame"] > 0 and c["pairs"] > 0 and c["sharded_phase_ms"] > 0 and "roofline" in c
 
 
 @pytest.mark.gpu
