@@ -521,10 +521,8 @@ class Scenario:
         stage = {k: g.max_over_ranks(v / reps) for k, v in acc.items()}
         rounds = [r for r in sc.round_stats() if r]
         cyc = sc.phase_cycles()
-        if cyc and sum(cyc) > 0:  # broad and narrow share one persistent kernel: split by its SM-cycle stamps
-            share = cyc[-1] / float(sum(cyc))
-            both = stage["broad"] + stage["narrow"]
-            stage["narrow"], stage["broad"] = both * share, both * (1.0 - share)
+        # broad and narrow phase are ONE kernel and the narrow phase runs inside the traversal's warps (a leaf pair is
+        # tested by the warp that finds it): stage["broad"] is the whole detection, stage["narrow"] stays 0
         g.barrier()
         return {"frame_ms": ms, "stage_ms": stage, "pairs": int(n_pairs), "candidates": int(n_cand), "bvtt_rounds": rounds,
                 "collide_phase_cycles": cyc, "gpu_launches": int(l1 - l0), "frames_timed": launches * self.frames_per_graph}

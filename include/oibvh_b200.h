@@ -210,8 +210,8 @@ int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_ca
 int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs);
 /* device view of the pair list of the last detection (for a collective gather by the caller) */
 int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs);
-/* SM-clock cycles CTA 0 of the detection kernel spent in each phase of the last detection: [0] seeding, [1..R]
- * the R expansion rounds that ran, [R+1] the barrier before the narrow phase, [R+2] its share of the narrow phase.
+/* SM-clock cycles CTA 0 of the detection kernel spent in each phase of the last detection: [0] seeding + the one grid
+ * barrier, [1] queue-driven traversal with the narrow phase fused in, [2] leaving the queue empty.
  * Returns the number of phases written. Replaces the reference's per-launch stopwatch (scene.cu:299-302, 419). */
 int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases, uint32_t* n_phases);
 /* device view of the counter block of the last detection: word 0 = candidates, word 1 = pairs (lets a caller chain
@@ -223,8 +223,8 @@ int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t 
 int oibvh_scene_device_counters(oibvh_scene* scene, const uint32_t** dev_counters);
 /* current capacity (records) of the device pair list returned by oibvh_scene_device_pairs */
 int oibvh_scene_pair_capacity(oibvh_scene* scene, uint32_t* capacity);
-/* per-round BVTT statistics of the last detection: tested[r] nodes were overlap-tested in round r.
- * Returns the number of rounds written (<= max_rounds). */
+/* BVTT statistics of the last detection: tested[l] = BVTT nodes taken from the work queue whose side-A node is at
+ * tree level l (the traversal has no rounds: it is queue-driven). Returns the number of levels written (<= max_rounds). */
 int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested, uint32_t max_rounds, uint32_t* n_rounds);
 
 /* Scene::convertToVertexArray (src/cuda/scene.cu:68-93) as a device-side gather: pair i of the last detection

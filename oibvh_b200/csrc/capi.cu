@@ -136,8 +136,7 @@ struct oibvh_scene
     ObjDesc* d_objs = nullptr;
     size_t d_objs_cap = 0;
     bool objs_dirty = true;
-    uint4* front[2] = {nullptr, nullptr};
-    uint4* cand = nullptr;
+    uint4* queue = nullptr; // BVTT work queue: every slot holds the empty marker (all bits set) between detections
     uint4* pairs = nullptr;
     uint32_t front_cap = 0, cand_cap = 0, pair_cap = 0;
     // Device counter block (CTR_WORDS). Once the work queues exist it is the HEAD of the pair-list allocation:
@@ -323,11 +322,9 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
 
 void scene_free_buffers(oibvh_scene* s)
 {
-    cudaFree(s->front[0]);
-    cudaFree(s->front[1]);
-    cudaFree(s->cand);
+    cudaFree(s->queue);
     cudaFree(s->pair_block);
-    s->front[0] = s->front[1] = s->cand = s->pairs = s->pair_block = nullptr;
+    s->queue = s->pairs = s->pair_block = nullptr;
     s->counters = s->counters_own;
 }
 
@@ -338,9 +335,13 @@ int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, u
     int rc;
     static_assert(CTR_WORDS * sizeof(uint32_t) % sizeof(uint4) == 0, "the counter block is a whole number of records");
     constexpr size_t kCtrRecords = CTR_WORDS * sizeof(uint32_t) / sizeof(uint4);
-    if ((rc = dev_alloc(&s->front[0], front_cap)) || (rc = dev_alloc(&s->front[1], front_cap)) ||
-        (rc = dev_alloc(&s->cand, cand_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)))
+    // (cand_cap is kept for the interface: candidates are tested by the warp that finds them and never stored)
+    if ((rc = dev_alloc(&s->queue, front_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)))
         return rc;
+    {
+        cudaError_t e = cudaMemsetAsync(s->queue, 0xff, sizeof(uint4) * (size_t)front_cap, s->ctx->stream);
+        if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+    }
     s->counters = reinterpret_cast<uint32_t*>(s->pair_block);
     s->pairs = s->pair_block + kCtrRecords;
     {
@@ -1369,9 +1370,9 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
         int rc = tree_flush_upload(t); // the narrow phase reads the positions
         if (rc) return rc;
     }
-    // One warp tests the 4^k descendant pairs of a node pair, 64 per iteration, so k = 3 costs one iteration per pair.
-    // The fronts grow geometrically towards the leaves; the cheapest schedule (measured) makes EVERY round after the
-    // first a 3-level round -- in particular the last, widest one -- and lets round 0 absorb the remainder.
+    // One warp tests the 4^k descendant pairs of a node pair, 64 per step, so k = 3 costs one step per pair. The
+    // front grows geometrically towards the leaves; the cheapest schedule (measured) makes EVERY hop after the first a
+    // 3-level hop -- in particular the last, widest one -- and lets the root pairs absorb the remainder.
     // expand_levels == 0 selects that schedule (entry_level is then ignored: both are hints, the pair set does not
     // depend on them); explicit values are honoured up to 5 (round 0) / 4 levels.
     uint32_t k0;
@@ -1389,9 +1390,7 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
         expand_levels = std::min(expand_levels, 4u);
         k0 = entry_level > 0 ? std::min(entry_level, 5u) : expand_levels;
     }
-    const uint32_t reached = std::min(k0, maxL);
-    const uint32_t rounds = 1 + (maxL - reached + expand_levels - 1) / expand_levels; // leaf pairs leave as candidates
-    if (rounds + 1 >= CTR_MAX_ROUNDS) return fail(OIBVH_ERR_INTERNAL, "too many traversal rounds (%u)", rounds);
+    const uint32_t rounds = CTR_MAX_ROUNDS - 1; // statistics: one counter per tree level
 
     MgpuArgs mg{};
     mg.mode = (uint32_t)s->mg_mode;
@@ -1417,9 +1416,8 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     {
         // broad and narrow phase run inside one persistent kernel; the stage clock covers both
         StageScope scope(ctx, OIBVH_STAGE_BROAD);
-        CU(launch_collide(ctx->collide_grid, s->d_objs, n_obj, s->front[0], s->front[1], s->front_cap, s->cand,
-                          s->cand_cap, s->pairs, s->pair_cap, s->counters, rounds, k0, expand_levels, s->rank,
-                          s->world, mg, st));
+        CU(launch_collide(ctx->collide_grid, s->d_objs, n_obj, s->queue, s->front_cap, s->pairs, s->pair_cap,
+                          s->counters, k0, expand_levels, s->rank, s->world, mg, st));
         count_launch(ctx);
     }
     s->enq_epochs.resize(s->trees.size());
@@ -1624,11 +1622,18 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
     {
         CU(cudaStreamSynchronize(ctx->stream));
         const uint32_t* h = scene->h_counters;
-        uint32_t max_front = 0;
-        for (uint32_t r = 0; r <= scene->last_rounds; r++) max_front = std::max(max_front, h[CTR_FRONT0 + r]);
-        if (h[CTR_OVERFLOW] & 8u) return fail(OIBVH_ERR_INTERNAL, "grid barrier timed out in the detection kernel");
+        const uint32_t max_front = h[CTR_Q_TAIL]; // records pushed (a lower bound when the traversal was cut short)
+        if (h[CTR_OVERFLOW] & 8u)
+        {
+            // the queue may hold stale records: put the empty marker back before anything else runs on it
+            if (scene->queue) cudaMemsetAsync(scene->queue, 0xff, sizeof(uint4) * (size_t)scene->front_cap, ctx->stream);
+            return fail(OIBVH_ERR_INTERNAL, "a wait timed out in the detection kernel");
+        }
         if (h[CTR_OVERFLOW] & 16u)
             return fail(OIBVH_ERR_INTERNAL, "multi-GPU detection: a rank did not open / finish the frame in time");
+        if (h[CTR_OVERFLOW] != 0 && scene->queue)
+            // an aborted traversal leaves records in the queue: restore the empty marker (regrowing does it too)
+            CU(cudaMemsetAsync(scene->queue, 0xff, sizeof(uint4) * (size_t)scene->front_cap, ctx->stream));
         if (h[CTR_OVERFLOW] != 0 && scene->mg_mode != 0)
             return fail(OIBVH_ERR_OVERFLOW, "multi-GPU detection: a work queue overflowed (flags %u); the queues of a "
                                             "multi-GPU scene are fixed -- oibvh_scene_reserve before oibvh_mgpu_export",
@@ -1641,8 +1646,7 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         }
         // a queue overflowed: grow (counts keep counting past the capacity, so they are lower bounds) and redo
         uint32_t fc = scene->front_cap, cc = scene->cand_cap, pc = scene->pair_cap;
-        if (h[CTR_OVERFLOW] & 1u) fc = grow_to(fc, max_front);
-        if (h[CTR_OVERFLOW] & 2u) cc = grow_to(cc, h[CTR_CANDIDATES]);
+        if (h[CTR_OVERFLOW] & 1u) fc = grow_to(fc, max_front); // every BVTT node of the traversal passes through the queue
         if (h[CTR_OVERFLOW] & 4u) pc = grow_to(pc, h[CTR_PAIRS]);
         if (fc == scene->front_cap && cc == scene->cand_cap && pc == scene->pair_cap)
             return fail(OIBVH_ERR_OVERFLOW, "work queues cannot grow further");
@@ -1776,7 +1780,7 @@ extern "C" int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles
     if (rc) return rc;
     const uint32_t* h = scene->h_counters;
     uint32_t stamps = h[CTR_TIME0 - 1];
-    if (stamps > (uint32_t)(CTR_WORDS - CTR_TIME0)) stamps = CTR_WORDS - CTR_TIME0;
+    if (stamps > (uint32_t)CTR_WORDS_TIME) stamps = CTR_WORDS_TIME;
     const uint32_t n = stamps ? std::min(max_phases, stamps - 1) : 0;
     for (uint32_t i = 0; i < n; i++) cycles[i] = h[CTR_TIME0 + i + 1] - h[CTR_TIME0 + i]; // wraps correctly
     *n_phases = n;
@@ -1803,7 +1807,7 @@ extern "C" int oibvh_scene_get_round_stats(oibvh_scene* scene, uint32_t* tested,
     REQUIRE(scene && tested && n_rounds, "NULL argument");
     int rc = oibvh_scene_get_counts(scene, nullptr, nullptr);
     if (rc) return rc;
-    const uint32_t n = std::min(max_rounds, scene->last_rounds);
+    const uint32_t n = std::min(max_rounds, (uint32_t)CTR_MAX_ROUNDS); // one entry per tree level of side A
     for (uint32_t r = 0; r < n; r++) tested[r] = scene->h_counters[CTR_FRONT0 + r];
     *n_rounds = n;
     return OIBVH_OK;

@@ -5,20 +5,22 @@
 //   candidate = both leaves with inclusively overlapping boxes       src/cuda/collide.cu:155-162
 //   narrow phase = SAT over n1, m1, e_i x f_j, e_i x n1, f_j x m1     src/utils/utils.cpp:71-169
 //                                                                    (== third/gProximity/cuda_intersect_tritri.h:350-434)
-// Design: the front lives in device memory as 16-byte (objA, objB, nodeA, nodeB) records with nodes addressed as
-// (level, position) so no implicit<->real conversion is needed; every warp tests 32 front nodes, prefix-sums the
-// fan-outs with shuffles, claims ONE range of the next front with a single atomic, and then writes that range
-// cooperatively (32 consecutive 16-byte records per store instruction). Front sizes never visit the host.
+// Design: BVTT nodes are 16-byte (objA, objB, nodeA, nodeB) records with tree nodes addressed as (level, position), so no
+// implicit<->real conversion is needed. The front is ONE work queue in device memory that the persistent warps of a
+// single cooperative launch fill and drain without grid barriers (see traverse_queue); the narrow phase runs inside the
+// same warps on the leaf pairs they find. Nothing visits the host between the seeds and the pair list.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace oibvh
 {
 
-// One persistent cooperative kernel runs the whole detection: seeds -> every expansion round -> narrow phase, with a
-// grid-wide barrier between phases, so a detection costs one launch and the per-round latency is one barrier
-// (~1 us) instead of a kernel boundary. One CTA of 1024 threads per SM (148 arrivals per barrier).
-constexpr int kColThreads = 1024;
+// One persistent cooperative kernel runs the whole detection: seeds -> ONE grid barrier -> queue-driven traversal with
+// the narrow phase fused in. One CTA of 1024 threads per SM.
+#ifndef OIBVH_COL_THREADS
+#define OIBVH_COL_THREADS 512
+#endif
+constexpr int kColThreads = OIBVH_COL_THREADS;
 constexpr int kColWarps = kColThreads / 32;
 
 __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, uint32_t i)
@@ -33,6 +35,47 @@ __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, ui
     d.T = b.z;
     d.L = b.w;
     return d;
+}
+
+// Queue records are published and consumed with single-copy-atomic 128-bit accesses (PTX .b128, STG/LDG.E.128.STRONG.GPU
+// on sm_100a): a consumer polling a slot sees either the empty marker or the whole record, so no per-record flag or
+// fence is needed. A slot is EMPTY while its first word is kQEmpty (objects are numbered below 2^32 - 1).
+constexpr uint32_t kQEmpty = 0xffffffffu;
+__device__ __forceinline__ void st_rec(uint4* p, const uint4& v)
+{
+    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], t;\n\t}" ::"l"(p),
+                 "l"(((uint64_t)v.y << 32) | v.x), "l"(((uint64_t)v.w << 32) | v.z)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_rec(const uint4* p)
+{
+    uint64_t lo, hi;
+    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+                 : "=l"(lo), "=l"(hi)
+                 : "l"(p)
+                 : "memory");
+    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+// Queue state = ONE 64-bit word: pushed records in the high half (the tail: the next free slot), finished items in the
+// low half. One atomic reserves slots, one atomic retires items, and because both hit the same address every
+// observer sees an exact snapshot of (pushed, finished) -- the termination test needs no fence.
+// Atomics on one address are served one at a time by its L2 slice (~1-2 cycles each): with a BVTT of 10^5 nodes, one
+// reserve and one retire per node would cost more than the traversal itself (measured: 264 K cycles). So a warp
+// keeps the items it has finished in a register and retires them TOGETHER with its next reservation (one atomic does
+// both), or when it runs out of work; retiring late only delays the detection of the end, never fakes it.
+__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counters, uint32_t n, uint32_t retire = 0)
+{
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_Q_STATE),
+                                             ((unsigned long long)n << 32) | retire);
+    return (uint32_t)(old >> 32);
+}
+// retire n items; true when every record ever pushed has been retired (nothing in flight, nothing can be pushed)
+__device__ __forceinline__ bool queue_retire(uint32_t* counters, uint32_t n)
+{
+    const unsigned long long now =
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_Q_STATE), (unsigned long long)n) + n;
+    return (uint32_t)(now >> 32) == (uint32_t)now;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -61,6 +104,7 @@ __device__ __forceinline__ uint4 seed_entry(uint32_t n_obj, uint64_t p)
 __device__ void seed_phase(float* __restrict__ s_roots, const ObjDesc* __restrict__ objs, uint32_t n_obj,
                            uint4* __restrict__ front, uint32_t front_cap, uint32_t* __restrict__ counters)
 {
+    // (`front` is the work queue: a slot is claimed from its tail counter and filled with one 128-bit store)
     uint32_t bshift = 8;
     auto tiles_of = [&](uint32_t sh) {
         const uint32_t nb = (n_obj + (1u << sh) - 1) >> sh;
@@ -122,13 +166,13 @@ __device__ void seed_phase(float* __restrict__ s_roots, const ObjDesc* __restric
             if (mask)
             {
                 uint32_t slot = 0;
-                if (lane == 0) slot = atomicAdd(counters + CTR_FRONT0, (uint32_t)__popc(mask));
+                if (lane == 0) slot = queue_reserve(counters, (uint32_t)__popc(mask));
                 slot = __shfl_sync(0xffffffffu, slot, 0);
                 if (hit)
                 {
                     const uint32_t dst = slot + __popc(mask & lanemask_lt());
                     if (dst < front_cap)
-                        front[dst] = make_uint4(i0 + ii, j0 + jj, 0u, 0u);
+                        st_rec(front + dst, make_uint4(i0 + ii, j0 + jj, 0u, 0u));
                     else
                         atomicOr(counters + CTR_OVERFLOW, 1u);
                 }
@@ -155,11 +199,11 @@ __device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        // release-arrive / acquire-poll (see grid_sync in common.cuh)
+        // release-arrive / relaxed polls + one acquire fence (see grid_sync in common.cuh)
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + CTR_BARRIER) : "memory");
         const uint32_t target = generation * gridDim.x;
         uint32_t spins = 0;
-        while (ld_acquire_gpu(counters + CTR_BARRIER) < target)
+        while (ld_relaxed_gpu(counters + CTR_BARRIER) < target)
         {
             if (++spins > (1u << 26))
             {
@@ -167,299 +211,11 @@ __device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters
                 break;
             }
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         s_value = __ldcg(read_after);
     }
     __syncthreads();
     return s_value;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// One round of BVTT expansion, warp-cooperative.
-//
-// A front entry is a node pair whose boxes are KNOWN to overlap (round 0: the untested root pairs). One warp takes
-// one pair, addresses the rectangle of descendants `levels` levels further down on each side (clamped to the leaf
-// level and to the nodes the level keeps), and its 32 lanes test the nA x nB descendant box pairs -- the 2^k + 2^k
-// boxes are two contiguous slices of the level arrays, so the loads are broadcast / L1 hits. Only overlapping
-// descendant pairs are emitted: to the next front, or to the candidate list when both sides reached the leaf level
-// (a candidate is by definition a leaf pair with overlapping boxes, src/cuda/collide.cu:155-162).
-// Emission is staged per warp in shared memory and flushed with ONE global atomic per ~200 records and
-// fully coalesced 16-byte stores; the grid is persistent (grid-stride over the front).
-// ---------------------------------------------------------------------------------------------------
-#ifndef OIBVH_STAGE_CAP
-#define OIBVH_STAGE_CAP 256
-#endif
-constexpr int kStageCap = OIBVH_STAGE_CAP; // records per warp staging buffer (4 KB), half per record kind
-static_assert(kStageCap / 2 >= 64, "one item emits up to 64 records of one kind");
-
-constexpr int kObjCache = 64; // object descriptors + level tables kept in shared memory (more: L1/L2 + arithmetic)
-
-__device__ __forceinline__ ObjDesc get_obj(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, uint32_t i)
-{
-    // (a compact shared-memory table of all objects was measured slower than these L1/L2 hits: it costs L1 capacity)
-    return i < (uint32_t)kObjCache ? s_objs[i] : load_obj(objs, i);
-}
-
-// level geometry of an object: from the shared-memory tables for cached objects, from arithmetic otherwise
-struct LevelView
-{
-    const uint32_t* off; // null -> compute
-    const uint32_t* cnt;
-    uint32_t T, L;
-    __device__ __forceinline__ uint32_t offset(uint32_t l) const { return off ? off[l] : level_offset(T, L, l); }
-    __device__ __forceinline__ uint32_t count(uint32_t l) const { return cnt ? cnt[l] : level_count(T, L, l); }
-};
-__device__ __forceinline__ LevelView level_view(const uint32_t* s_lv, uint32_t obj, const ObjDesc& d)
-{
-    LevelView v;
-    v.T = d.T;
-    v.L = d.L;
-    v.off = obj < (uint32_t)kObjCache ? s_lv + obj * 64 : nullptr;
-    v.cnt = obj < (uint32_t)kObjCache ? s_lv + obj * 64 + 32 : nullptr;
-    return v;
-}
-
-// Set-up and testing are split. Everything that depends only on the item (descriptor fetch, level geometry,
-// rectangle clamping: ~200 instructions) would be warp-uniform work, issued once per item for 32 identical lanes, and
-// made wide fronts instruction-bound. So a warp takes a BATCH of up to 32 items: lane l sets up item l (phase 1, 32
-// different items per issued instruction), then the warp walks the batch and broadcasts each item's ten parameters
-// with shuffles (phase 2: index arithmetic, four box loads per lane, tests, staging). The batch size shrinks with
-// the front so that small fronts still spread over every warp of the grid. Measured: -45 % on fronts of 10^5..10^6
-// items, unchanged on latency-bound fronts of a few hundred.
-__device__ void expand_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32_t* s_lv,
-                             const ObjDesc* __restrict__ objs, const uint4* in,
-                                     uint4* out, uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint32_t* counters,
-                                     uint32_t round, uint32_t front_size, uint32_t levels, uint32_t rank, uint32_t world,
-                                     uint32_t n_obj)
-{
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const bool computed_seeds = (round == 0 && in == nullptr);
-    const uint32_t n = computed_seeds ? front_size : min(front_size, front_cap);
-    uint32_t* next_count = counters + CTR_FRONT0 + round + 1;
-    const uint32_t total_warps = gridDim.x * kColWarps;
-    constexpr uint32_t kHalf = kStageCap / 2;
-    uint4* stage = s_stage + warp * kStageCap;
-    uint32_t staged_f = 0, staged_c = 0; // warp-uniform
-
-    auto flush = [&](bool is_cand) {
-        const uint32_t staged = is_cand ? staged_c : staged_f;
-        if (staged == 0) return;
-        __syncwarp();
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(is_cand ? counters + CTR_CANDIDATES : next_count, staged);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        uint4* dst = is_cand ? cand : out;
-        const uint4* src = stage + (is_cand ? kHalf : 0u);
-        const uint32_t cap = is_cand ? cand_cap : front_cap;
-        if (base + staged > cap && lane == 0) atomicOr(counters + CTR_OVERFLOW, is_cand ? 2u : 1u);
-        for (uint32_t j = lane; j < staged; j += 32)
-            if (base + j < cap) dst[base + j] = src[j];
-        __syncwarp();
-        if (is_cand)
-            staged_c = 0;
-        else
-            staged_f = 0;
-    };
-
-    const uint32_t gshift = 2 * levels > 6 ? 2 * levels - 6 : 0; // log2(64-combination groups per pair)
-    const uint32_t items = n << gshift;                          // n < 2^26, gshift <= 4
-    const uint32_t batch = min(32u, max(1u, (items + total_warps - 1) / total_warps));
-    const bool sharded = world > 1 && round == 0;
-    // fronts are produced by other SMs inside this same launch: read them through L2 (ld.cg); the entries of the
-    // NEXT batch are fetched before the current one is processed (one round trip off the critical path)
-    auto entry = [&](uint32_t w) {
-        if (!(lane < batch && w < items)) return make_uint4(0, 0, 0, 0);
-        return computed_seeds ? seed_entry(n_obj, w >> gshift) : __ldcg(in + (w >> gshift));
-    };
-    uint32_t wb = (blockIdx.x * kColWarps + warp) * batch;
-    uint4 it_next = entry(wb + lane);
-    for (; wb < items; wb += total_warps * batch)
-    {
-        // ---- phase 1: lane l prepares item wb + l ----
-        const uint32_t w = wb + lane;
-        bool valid = lane < batch && w < items;
-        const uint4 it = it_next;
-        it_next = entry(w + total_warps * batch);
-        uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, key = 0;
-        uint64_t ptrA = 0, ptrB = 0;
-        if (valid)
-        {
-            const uint32_t p = w >> gshift, group = w & ((1u << gshift) - 1);
-            const ObjDesc A = get_obj(s_objs, objs, it.x), B = get_obj(s_objs, objs, it.y);
-            const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
-            const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
-            const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
-            const uint32_t da = min(levels, A.L - la), db = min(levels, B.L - lb);
-            const uint32_t lca = la + da, lcb = lb + db;
-            const uint32_t fa = pa << da, fb = pb << db;
-            const uint32_t nA = min(1u << da, va.count(lca) - fa);
-            const uint32_t nB = min(1u << db, vb.count(lcb) - fb);
-            const uint32_t combos = nA * nB; // <= 1024
-            valid = group * 64 < combos;     // clamped rectangle: nothing in this group
-            if (valid && computed_seeds)
-            {
-                // computed root pairs are untested: prune object pairs whose root boxes are disjoint
-                const Box ra = load_box(reinterpret_cast<const float2*>(A.nodes), va.offset(la) + pa);
-                const Box rb = load_box(reinterpret_cast<const float2*>(B.nodes), vb.offset(lb) + pb);
-                valid = box_overlap(ra, rb);
-            }
-            const bool to_cand = (lca == A.L) && (lcb == B.L);
-            ptrA = (uint64_t)A.nodes;
-            ptrB = (uint64_t)B.nodes;
-            baseA = va.offset(lca) + fa;
-            baseB = vb.offset(lcb) + fb;
-            ex = it.x;
-            ey = it.y;
-            // emitted node ids are za + ia / zb + ib (fa, fb have their low da / db bits clear)
-            za = to_cand ? fa : ((lca << kNodeLevelShift) | fa);
-            zb = to_cand ? fb : ((lcb << kNodeLevelShift) | fb);
-            meta = combos | (nB << 11) | (db << 17) | ((nB == (1u << db)) ? 1u << 20 : 0u) | (to_cand ? 1u << 21 : 0u) |
-                   (group << 22);
-            // round 0 deals the seed rectangle round-robin to the shards, keyed by the object pair's linear index
-            // (not by the nondeterministic slot of a seeded entry)
-            if (sharded) key = computed_seeds ? p : pair_linear(n_obj, it.x, it.y);
-        }
-        // ---- phase 2: the warp walks the prepared items ----
-        for (uint32_t todo = __ballot_sync(0xffffffffu, valid); todo; todo &= todo - 1)
-        {
-            const int k = __ffs(todo) - 1;
-            const uint32_t mk = __shfl_sync(0xffffffffu, meta, k);
-            const uint32_t combos = mk & 0x7ffu, nB = (mk >> 11) & 63u, db = (mk >> 17) & 7u, group = mk >> 22;
-            const bool to_cand = (mk >> 21) & 1u;
-            const float2* nodesA = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrA, k));
-            const float2* nodesB = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrB, k));
-            const uint32_t bA = __shfl_sync(0xffffffffu, baseA, k), bB = __shfl_sync(0xffffffffu, baseB, k);
-            const uint32_t c0 = group * 64 + lane, c1 = c0 + 32;
-            bool hit0 = c0 < combos, hit1 = c1 < combos;
-            if (sharded)
-            {
-                const uint32_t kk = __shfl_sync(0xffffffffu, key, k);
-                hit0 = hit0 && ((kk + c0) % world) == rank;
-                hit1 = hit1 && ((kk + c1) % world) == rank;
-            }
-            // nB is a power of two unless the rectangle is clamped by the end of the level (warp-uniform either way)
-            uint32_t ia0, ib0, ia1, ib1;
-            if ((mk >> 20) & 1u)
-            {
-                ia0 = c0 >> db;
-                ib0 = c0 & (nB - 1);
-                ia1 = c1 >> db;
-                ib1 = c1 & (nB - 1);
-            }
-            else
-            {
-                ia0 = c0 / nB;
-                ib0 = c0 - ia0 * nB;
-                ia1 = c1 / nB;
-                ib1 = c1 - ia1 * nB;
-            }
-            Box a0, b0, a1, b1;
-            if (hit0)
-            {
-                a0 = load_box(nodesA, bA + ia0);
-                b0 = load_box(nodesB, bB + ib0);
-            }
-            if (hit1)
-            {
-                a1 = load_box(nodesA, bA + ia1);
-                b1 = load_box(nodesB, bB + ib1);
-            }
-            if (hit0) hit0 = box_overlap(a0, b0);
-            if (hit1) hit1 = box_overlap(a1, b1);
-            const uint32_t mask0 = __ballot_sync(0xffffffffu, hit0), mask1 = __ballot_sync(0xffffffffu, hit1);
-            const uint32_t cnt0 = __popc(mask0), cnt = cnt0 + __popc(mask1);
-            if (cnt == 0) continue; // warp-uniform
-            if ((to_cand ? staged_c : staged_f) + cnt > kHalf) flush(to_cand);
-            const uint32_t exk = __shfl_sync(0xffffffffu, ex, k), eyk = __shfl_sync(0xffffffffu, ey, k);
-            const uint32_t zak = __shfl_sync(0xffffffffu, za, k), zbk = __shfl_sync(0xffffffffu, zb, k);
-            uint4* st = stage + (to_cand ? kHalf + staged_c : staged_f);
-            if (hit0) st[__popc(mask0 & lanemask_lt())] = make_uint4(exk, eyk, zak + ia0, zbk + ib0);
-            if (hit1) st[cnt0 + __popc(mask1 & lanemask_lt())] = make_uint4(exk, eyk, zak + ia1, zbk + ib1);
-            if (to_cand)
-                staged_c += cnt;
-            else
-                staged_f += cnt;
-        }
-    }
-    flush(false);
-    flush(true);
-}
-
-// Dense round 0 for scenes of very few objects (two-body scenes): instead of walking down from the root pair through
-// several latency-bound rounds of a handful of items (each costs a grid barrier plus ~4 dependent L2 round trips,
-// ~4.5 us, whatever its size), ALL node pairs (a, b) at level `k0` of an object pair are tested directly, spread over
-// every warp of the grid: 4^8 = 65 K .. 4^11 = 4 M box tests are less work than the rounds they replace. A level is a
-// contiguous slice, so a warp's 32 consecutive combinations read one broadcast box of A and 32 consecutive boxes of B.
-// Same emission path (per-warp staging, one atomic per flush) and the same shard rule as expand_phase.
-__device__ void dense_seed_phase(uint4* s_stage, const ObjDesc* s_objs, const uint32_t* s_lv,
-                                 const ObjDesc* __restrict__ objs, uint4* out, uint32_t front_cap, uint4* cand,
-                                 uint32_t cand_cap, uint32_t* counters, uint32_t n_pairs, uint32_t k0, uint32_t rank,
-                                 uint32_t world, uint32_t n_obj)
-{
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t* next_count = counters + CTR_FRONT0 + 1;
-    const uint32_t total_warps = gridDim.x * kColWarps;
-    constexpr uint32_t kHalf = kStageCap / 2;
-    uint4* stage = s_stage + warp * kStageCap;
-    uint32_t staged = 0; // warp-uniform; one kind per object pair (flushed before the kind can change)
-    auto flush = [&](bool is_cand) {
-        if (staged == 0) return;
-        __syncwarp();
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(is_cand ? counters + CTR_CANDIDATES : next_count, staged);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        uint4* dst = is_cand ? cand : out;
-        const uint32_t cap = is_cand ? cand_cap : front_cap;
-        if (base + staged > cap && lane == 0) atomicOr(counters + CTR_OVERFLOW, is_cand ? 2u : 1u);
-        for (uint32_t j = lane; j < staged; j += 32)
-            if (base + j < cap) dst[base + j] = stage[j];
-        __syncwarp();
-        staged = 0;
-    };
-    const uint32_t gw = blockIdx.x * kColWarps + warp;
-    for (uint32_t p = 0; p < n_pairs; p++)
-    {
-        const uint4 it = seed_entry(n_obj, p);
-        const ObjDesc A = get_obj(s_objs, objs, it.x), B = get_obj(s_objs, objs, it.y);
-        const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
-        const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
-        const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
-        if (!box_overlap(load_box(nodesA, 0), load_box(nodesB, 0))) continue; // disjoint roots (warp-uniform)
-        const uint32_t ka = min(k0, A.L), kb = min(k0, B.L);
-        const uint32_t nA = va.count(ka), nB = vb.count(kb), baseA = va.offset(ka), baseB = vb.offset(kb);
-        const bool to_cand = (ka == A.L) && (kb == B.L);
-        const uint32_t za = to_cand ? 0u : (ka << kNodeLevelShift), zb = to_cand ? 0u : (kb << kNodeLevelShift);
-        const uint32_t total = nA * nB; // <= 4^11
-        for (uint32_t c0 = gw * 64; c0 < total; c0 += total_warps * 64)
-        {
-            const uint32_t c[2] = {c0 + lane, c0 + 32 + lane};
-            bool hit[2];
-            uint32_t ia[2], ib[2];
-            Box a[2], b[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++)
-            {
-                hit[u] = c[u] < total && (world == 1 || ((p + c[u]) % world) == rank);
-                ia[u] = c[u] / nB;
-                ib[u] = c[u] - ia[u] * nB;
-                if (hit[u])
-                {
-                    a[u] = load_box(nodesA, baseA + ia[u]);
-                    b[u] = load_box(nodesB, baseB + ib[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++)
-                if (hit[u]) hit[u] = box_overlap(a[u], b[u]);
-            const uint32_t mask0 = __ballot_sync(0xffffffffu, hit[0]), mask1 = __ballot_sync(0xffffffffu, hit[1]);
-            const uint32_t cnt0 = __popc(mask0), cnt = cnt0 + __popc(mask1);
-            if (cnt == 0) continue; // warp-uniform
-            if (staged + cnt > kHalf) flush(to_cand);
-            if (hit[0]) stage[staged + __popc(mask0 & lanemask_lt())] = make_uint4(it.x, it.y, za + ia[0], zb + ib[0]);
-            if (hit[1]) stage[staged + cnt0 + __popc(mask1 & lanemask_lt())] = make_uint4(it.x, it.y, za + ia[1], zb + ib[1]);
-            staged += cnt;
-        }
-        flush(to_cand);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -552,28 +308,69 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
     return r;
 }
 
-// REMOTE = this rank is not the gathering rank: hits are appended to the ROOT's pair list through the peer mapping
-// (one system-scope atomic per warp claims the slots, then 16-byte stores over NVLink); the local counter still
-// counts this rank's own hits.
-template <bool REMOTE>
-__device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, const uint4* cand, uint32_t cand_cap,
-                             uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* counters, uint32_t n_cand,
-                             uint32_t* root_counters)
+constexpr int kObjCache = 64; // object descriptors + level tables kept in shared memory (more: L1/L2 + arithmetic)
+
+__device__ __forceinline__ ObjDesc get_obj(const ObjDesc* s_objs, const ObjDesc* __restrict__ objs, uint32_t i)
 {
-    const uint32_t lane = lane_id();
-    const uint32_t n = min(n_cand, cand_cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounded = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride)
+    // (a compact shared-memory table of all objects was measured slower than these L1/L2 hits: it costs L1 capacity)
+    return i < (uint32_t)kObjCache ? s_objs[i] : load_obj(objs, i);
+}
+
+// Everything a warp needs to emit: the queue, the pair list (local, or the gathering rank's through the peer mapping),
+// the counters, and its two staging areas in shared memory.
+#ifndef OIBVH_STAGE_CAP
+#define OIBVH_STAGE_CAP 256
+#endif
+constexpr int kStageCap = OIBVH_STAGE_CAP; // records per warp staging buffer (4 KB), half per record kind
+constexpr uint32_t kHalf = kStageCap / 2;
+static_assert(kStageCap / 2 >= 64, "one item emits up to 64 records of one kind");
+
+// CTA-uniform part, kept in SHARED memory (one copy per CTA, read by broadcast loads) so that it does not sit in ~14
+// registers of every thread across the traversal loop -- the kernel runs at the 64-register cap of a 1024-thread CTA
+struct EmitShared
+{
+    uint4* queue;        // work queue (BVTT nodes known to overlap)
+    uint4* pairs;        // pair list: local, or rank 0's (remote)
+    uint32_t* counters;  // this scene's counter block
+    uint32_t* pair_ctr;  // where pair slots are claimed: counters (local) or rank 0's counter block (remote)
+    const ObjDesc* objs;
+    uint32_t queue_cap;
+    uint32_t pair_cap;
+    uint32_t remote;
+    uint32_t pad;
+    ObjDesc s_objs[kObjCache];
+};
+struct Emit
+{
+    const EmitShared& sh;
+    uint4* stage;                // this warp's staging: [0, kHalf) queue records, [kHalf, 2 kHalf) candidates
+    uint32_t staged_f, staged_c; // warp-uniform
+    uint32_t retire;             // finished items not yet retired (lane 0)
+    uint32_t tail_seen;          // latest queue tail this warp has seen (lane 0): sizes its next claim
+    __device__ __forceinline__ Emit(const EmitShared& s, uint4* st)
+        : sh(s), stage(st), staged_f(0), staged_c(0), retire(0), tail_seen(0)
     {
+    }
+};
+
+// Narrow phase of the staged candidates (leaf pairs with overlapping boxes, src/cuda/collide.cu:155-162), by the warp
+// that found them: no candidate list in global memory, no barrier, no second pass. Hits are compacted with a ballot
+// and one atomic per 32 candidates; a remote rank claims its slots in rank 0's list with a system-scope atomic and
+// writes them over NVLink.
+#ifndef OIBVH_SAT_INLINE
+#define OIBVH_SAT_INLINE __noinline__
+#endif
+__device__ OIBVH_SAT_INLINE void narrow_staged(const EmitShared& sh, const uint4* src, uint32_t n, uint32_t lane)
+{
+    for (uint32_t base = 0; base < n; base += 32)
+    {
+        const uint32_t i = base + lane;
         bool hit = false;
         uint4 c = make_uint4(0, 0, 0, 0);
         if (i < n)
         {
-            c = __ldcg(cand + i);
-            // full descriptors (faces, vertices): shared-memory cache for the first objects, global otherwise
-            const ObjDesc A = c.x < (uint32_t)kObjCache ? s_objs[c.x] : load_obj(objs, c.x);
-            const ObjDesc B = c.y < (uint32_t)kObjCache ? s_objs[c.y] : load_obj(objs, c.y);
+            c = src[i];
+            const ObjDesc A = get_obj(sh.s_objs, sh.objs, c.x), B = get_obj(sh.s_objs, sh.objs, c.y);
             const uint32_t* fa = A.faces + 3ull * c.z;
             const uint32_t* fb = B.faces + 3ull * c.w;
             const V3 P1 = load_v3(A.pos, __ldg(fa)), P2 = load_v3(A.pos, __ldg(fa + 1)), P3 = load_v3(A.pos, __ldg(fa + 2));
@@ -583,30 +380,471 @@ __device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ 
         const uint32_t mask = __ballot_sync(0xffffffffu, hit);
         if (mask)
         {
-            uint32_t base = 0;
+            uint32_t slot = 0;
             if (lane == 0)
             {
-                if (REMOTE)
+                if (sh.remote)
                 {
-                    atomicAdd(counters + CTR_PAIRS, (uint32_t)__popc(mask)); // this rank's own count
-                    base = atomicAdd_system(root_counters + CTR_PAIRS, (uint32_t)__popc(mask));
+                    atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask)); // this rank's own count
+                    slot = atomicAdd_system(sh.pair_ctr + CTR_PAIRS, (uint32_t)__popc(mask));
                 }
                 else
-                    base = atomicAdd(counters + CTR_PAIRS, (uint32_t)__popc(mask));
+                    slot = atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask));
             }
-            base = __shfl_sync(0xffffffffu, base, 0);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
             if (hit)
             {
-                const uint32_t dst = base + __popc(mask & lanemask_lt());
-                if (dst < pair_cap)
-                    pairs[dst] = c; // {bvhA, bvhB, triA, triB} == int_tri_pair_node_t
-                else if (REMOTE)
-                    atomicOr_system(root_counters + CTR_OVERFLOW, 4u);
+                const uint32_t dst = slot + __popc(mask & lanemask_lt());
+                if (dst < sh.pair_cap)
+                    sh.pairs[dst] = c; // {bvhA, bvhB, triA, triB} == int_tri_pair_node_t
+                else if (sh.remote)
+                    atomicOr_system(sh.pair_ctr + CTR_OVERFLOW, 4u);
                 else
-                    atomicOr(counters + CTR_OVERFLOW, 4u);
+                    atomicOr(sh.counters + CTR_OVERFLOW, 4u);
             }
         }
     }
+    if (lane == 0) atomicAdd(sh.counters + CTR_CANDIDATES, n);
+}
+__device__ __forceinline__ void flush_candidates(Emit& e, uint32_t lane)
+{
+    if (e.staged_c == 0) return;
+    __syncwarp();
+    narrow_staged(e.sh, e.stage + kHalf, e.staged_c, lane);
+    __syncwarp();
+    e.staged_c = 0;
+}
+
+// Push the staged BVTT nodes: ONE atomic claims the slots, each record leaves as one 128-bit store. A queue that is
+// full sets the overflow flag AND stops the traversal (the host regrows the queue and repeats the detection).
+__device__ __forceinline__ void flush_queue(Emit& e, uint32_t lane)
+{
+    const uint32_t n = e.staged_f;
+    if (n == 0) return;
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0)
+    {
+        base = queue_reserve(e.sh.counters, n, e.retire); // the pending retirements ride along
+        e.retire = 0;
+        e.tail_seen = base + n;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > e.sh.queue_cap && lane == 0)
+    {
+        atomicOr(e.sh.counters + CTR_OVERFLOW, 1u);
+        st_relaxed_gpu(e.sh.counters + CTR_Q_STOP, 1u);
+    }
+    for (uint32_t j = lane; j < n; j += 32)
+        if (base + j < e.sh.queue_cap) st_rec(e.sh.queue + base + j, e.stage[j]);
+    __syncwarp();
+    e.staged_f = 0;
+}
+
+// stage up to 64 overlapping descendant pairs of one item (two per lane) as queue records or candidates
+__device__ __forceinline__ void stage_hits(Emit& e, uint32_t lane, bool to_cand, bool hit0, bool hit1, const uint4& r0,
+                                           const uint4& r1)
+{
+    const uint32_t mask0 = __ballot_sync(0xffffffffu, hit0), mask1 = __ballot_sync(0xffffffffu, hit1);
+    const uint32_t cnt0 = __popc(mask0), cnt = cnt0 + __popc(mask1);
+    if (cnt == 0) return; // warp-uniform
+    if (to_cand)
+    {
+        if (e.staged_c + cnt > kHalf) flush_candidates(e, lane);
+    }
+    else if (e.staged_f + cnt > kHalf)
+        flush_queue(e, lane);
+    uint4* st = e.stage + (to_cand ? kHalf + e.staged_c : e.staged_f);
+    if (hit0) st[__popc(mask0 & lanemask_lt())] = r0;
+    if (hit1) st[cnt0 + __popc(mask1 & lanemask_lt())] = r1;
+    if (to_cand)
+        e.staged_c += cnt;
+    else
+        e.staged_f += cnt;
+}
+
+// level geometry of an object: from the shared-memory tables for cached objects, from arithmetic otherwise
+struct LevelView
+{
+    const uint32_t* off; // null -> compute
+    const uint32_t* cnt;
+    uint32_t T, L;
+    __device__ __forceinline__ uint32_t offset(uint32_t l) const { return off ? off[l] : level_offset(T, L, l); }
+    __device__ __forceinline__ uint32_t count(uint32_t l) const { return cnt ? cnt[l] : level_count(T, L, l); }
+};
+__device__ __forceinline__ LevelView level_view(const uint32_t* s_lv, uint32_t obj, const ObjDesc& d)
+{
+    LevelView v;
+    v.T = d.T;
+    v.L = d.L;
+    v.off = obj < (uint32_t)kObjCache ? s_lv + obj * 64 : nullptr;
+    v.cnt = obj < (uint32_t)kObjCache ? s_lv + obj * 64 + 32 : nullptr;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Seeding of scenes with few object pairs
+// ---------------------------------------------------------------------------------------------------
+// Root pairs: global warp w tests the root boxes of object pairs w, w + W, ... and queues the overlapping ones.
+__device__ void root_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs, uint32_t n_obj)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t total = gridDim.x * kColWarps * 32;
+    for (uint32_t p0 = (blockIdx.x * kColWarps + warp) * 32; p0 < n_pairs; p0 += total)
+    {
+        const uint32_t p = p0 + lane;
+        bool hit = false;
+        uint4 it = make_uint4(0, 0, 0, 0);
+        if (p < n_pairs)
+        {
+            it = seed_entry(n_obj, p);
+            const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
+            hit = box_overlap(load_box(reinterpret_cast<const float2*>(A.nodes), 0),
+                              load_box(reinterpret_cast<const float2*>(B.nodes), 0));
+        }
+        stage_hits(e, lane, false, hit, false, it, it);
+    }
+    flush_queue(e, lane);
+}
+
+// Dense seeding for scenes of very few objects (two-body scenes): instead of walking down from the root pair through
+// several latency-bound hops of a handful of items, ALL node pairs (a, b) at level `k0` of an object pair are tested
+// directly, spread over every warp of the grid: 4^8 = 65 K .. 4^11 = 4 M box tests are less work than the hops they
+// replace. A level is a contiguous slice, so a warp's 32 consecutive combinations read one broadcast box of A and 32
+// consecutive boxes of B. `rank`/`world` deal the combinations to the shards.
+__device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs, uint32_t k0, uint32_t rank,
+                                 uint32_t world, uint32_t n_obj)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t total_warps = gridDim.x * kColWarps;
+    const uint32_t gw = blockIdx.x * kColWarps + warp;
+    for (uint32_t p = 0; p < n_pairs; p++)
+    {
+        const uint4 it = seed_entry(n_obj, p);
+        const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
+        const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
+        const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
+        const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
+        if (!box_overlap(load_box(nodesA, 0), load_box(nodesB, 0))) continue; // disjoint roots (warp-uniform)
+        const uint32_t ka = min(k0, A.L), kb = min(k0, B.L);
+        const uint32_t nA = va.count(ka), nB = vb.count(kb), baseA = va.offset(ka), baseB = vb.offset(kb);
+        const bool to_cand = (ka == A.L) && (kb == B.L);
+        const uint32_t za = to_cand ? 0u : (ka << kNodeLevelShift), zb = to_cand ? 0u : (kb << kNodeLevelShift);
+        const uint32_t total = nA * nB; // <= 4^11
+        for (uint32_t c0 = gw * 64; c0 < total; c0 += total_warps * 64)
+        {
+            const uint32_t c[2] = {c0 + lane, c0 + 32 + lane};
+            bool hit[2];
+            uint32_t ia[2], ib[2];
+            Box a[2], b[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+            {
+                hit[u] = c[u] < total && (world == 1 || ((p + c[u]) % world) == rank);
+                ia[u] = c[u] / nB;
+                ib[u] = c[u] - ia[u] * nB;
+                if (hit[u])
+                {
+                    a[u] = load_box(nodesA, baseA + ia[u]);
+                    b[u] = load_box(nodesB, baseB + ib[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (hit[u]) hit[u] = box_overlap(a[u], b[u]);
+            stage_hits(e, lane, to_cand, hit[0], hit[1], make_uint4(it.x, it.y, za + ia[0], zb + ib[0]),
+                       make_uint4(it.x, it.y, za + ia[1], zb + ib[1]));
+        }
+    }
+    flush_queue(e, lane);
+    flush_candidates(e, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Queue-driven BVTT traversal, warp-cooperative, no grid barriers.
+//
+// A queue record is a node pair whose boxes are KNOWN to overlap (root pairs: tested by the seeding). A warp owns the
+// slots it claims from the head counter -- up to 32 at a time when the backlog is long, one when it is short, so that
+// a front of a few hundred items still spreads over every warp of the chip -- and polls them until their records
+// appear (slots are filled in claim order by whoever emits next, so an idle warp is handed the very next node that is
+// produced). For each item the warp addresses the rectangle of descendants `levels` levels further down on each side
+// (clamped to the leaf level and to the nodes the level keeps) and its 32 lanes test the nA x nB descendant box
+// pairs; only overlapping pairs are emitted -- back into the queue, or, when both sides reached the leaf level, to
+// the warp's candidate staging area, whose triangle pairs it tests itself (flush_candidates).
+// Set-up and testing are split: what depends only on the item (descriptor fetch, level geometry, rectangle clamping:
+// ~200 instructions) is done by lane l for item l of the batch, then the warp walks the batch broadcasting each
+// item's parameters by shuffle.
+// Termination: pushed and finished records are the two halves of one 64-bit counter (queue_reserve / queue_retire); a
+// warp pushes everything its batch produced BEFORE it retires the batch, so the warp whose retirement makes the halves
+// equal knows that nothing is in flight and nothing can be pushed any more: it raises the stop flag. The hop latency is ~4 dependent L2 round trips
+// (claim, record, boxes, push) instead of a grid barrier on top of them, and hops of different subtrees overlap.
+// ---------------------------------------------------------------------------------------------------
+#ifdef OIBVH_PROFILE
+// where the traversal's warps spend their time (summed over all warps, lane 0's clock): [0] window, [1] polls that
+// found nothing, [2] set-up + box tests + staging, [3] queue pushes, [4] narrow phase, [5] total, [6] polls that found
+// records, [7] set-up alone; counts: [9] empty polls, [10] batches, [11] items, [12] candidate flushes
+__device__ unsigned long long g_col_prof[16];
+extern "C" int oibvh_debug_collide_profile(unsigned long long* out, int reset)
+{
+    if (reset)
+    {
+        unsigned long long z[16] = {};
+        return (int)cudaMemcpyToSymbol(g_col_prof, z, sizeof(z));
+    }
+    return (int)cudaMemcpyFromSymbol(out, g_col_prof, sizeof(g_col_prof));
+}
+#define COL_T(var) const long long var = clock64()
+#define COL_ADD(slot, val)                                                                                         \
+    do                                                                                                             \
+    {                                                                                                              \
+        if (lane == 0) prof[slot] += (unsigned long long)(val);                                                    \
+    } while (0)
+#else
+#define COL_T(var)
+#define COL_ADD(slot, val)
+#endif
+
+__device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, volatile uint32_t* s_ctl,
+                               uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, uint32_t n_obj,
+                               uint32_t seeded)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+#ifdef OIBVH_PROFILE
+    unsigned long long prof[16] = {};
+    const long long t_begin = clock64();
+#endif
+    e.tail_seen = seeded;
+    e.retire = 0;
+    const uint32_t total_warps = gridDim.x * kColWarps;
+    uint32_t* const ctr = e.sh.counters;
+    // Slots are owned statically, round-robin: global warp w owns slots w, w + W, w + 2 W, ... (W = warps of the grid).
+    // No head counter, no claim atomics (measured: thousands of warps claiming from one counter waited 5-7 K cycles per
+    // claim -- an L2 slice serves same-address atomics a few cycles apart), and the nodes of every hop are dealt evenly
+    // to the warps. A warp looks at a window of its next slots (one while the queue is short, up to 32 once there are
+    // several nodes per warp) and takes the filled prefix.
+    const uint32_t gw = blockIdx.x * kColWarps + warp;
+    uint32_t next = 0; // this warp's next slot is gw + next * W
+    for (;;)
+    {
+        COL_T(t0);
+        // ---- wait for this warp's next slot. Lane 0 spins on the first word of the record with as few instructions
+        // as possible: 32 idle warps per SM in a fat polling loop eat the issue slots of the warps that have work
+        // (measured: every phase of the traversal 3-5x slower); the other lanes wait at the shuffle below. ----
+        uint32_t state = 0; // 0 = a record is there, 1 = the traversal is over
+        if (lane == 0)
+        {
+            const uint64_t slot0 = (uint64_t)gw + (uint64_t)next * total_warps;
+            if (slot0 < e.sh.queue_cap)
+            {
+                const uint32_t* first = reinterpret_cast<const uint32_t*>(e.sh.queue + (uint32_t)slot0);
+                uint32_t spins = 0;
+                while (ld_relaxed_gpu(first) == kQEmpty)
+                {
+                    if ((++spins & 3u) != 0) continue;
+                    COL_ADD(9, 4);
+                    // every fourth poll: housekeeping.
+                    // (1) Out of work for a while: retire what this warp has finished (it may be the last one). Not at
+                    //     the first empty poll: between two hops every warp is briefly idle, and thousands of
+                    //     retirements at once would queue up on the counter the pushes need.
+                    if (e.retire)
+                    {
+                        if (queue_retire(ctr, e.retire))
+                        {
+                            st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
+                            s_ctl[0] = 1u;
+                        }
+                        e.retire = 0;
+                    }
+                    // (2) Thousands of idle warps must NOT poll the stop flag and the tail in global memory: those two
+                    //     words (the tail shares its line with the counter every push hits) would saturate their L2
+                    //     slice. One warp per CTA at a time -- the one whose number matches the current 2 K-cycle window
+                    //     -- refreshes a copy in shared memory; everybody else reads that.
+                    if ((((uint32_t)clock64() >> 11) % kColWarps) == warp)
+                    {
+                        s_ctl[1] = ld_relaxed_gpu(ctr + CTR_Q_TAIL);
+                        if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) s_ctl[0] = 1u;
+                    }
+                    if (s_ctl[0])
+                    {
+                        state = 1;
+                        break;
+                    }
+                    if (spins > (1u << 22))
+                    {
+                        atomicOr(ctr + CTR_OVERFLOW, 8u); // nothing arrived for seconds: report instead of hanging
+                        st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
+                        s_ctl[0] = 1u;
+                        state = 1;
+                        break;
+                    }
+                }
+            }
+            else
+            {
+                // this warp's slots are exhausted (the queue is full): retire, then wait for the end
+                if (e.retire)
+                {
+                    if (queue_retire(ctr, e.retire))
+                    {
+                        st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
+                        s_ctl[0] = 1u;
+                    }
+                    e.retire = 0;
+                }
+                uint32_t spins = 0;
+                while (!s_ctl[0] && ++spins < (1u << 22))
+                {
+                    if ((((uint32_t)clock64() >> 11) % kColWarps) == warp && ld_relaxed_gpu(ctr + CTR_Q_STOP))
+                        s_ctl[0] = 1u;
+                    __nanosleep(500);
+                }
+                state = 1;
+            }
+        }
+        state = __shfl_sync(0xffffffffu, state, 0);
+        COL_T(t1);
+        COL_ADD(1, t1 - t0);
+        if (state) break;
+        // ---- take the filled prefix of a window of this warp's next slots: one while the queue is short, up to 32
+        // once there are several nodes per warp (records of different producers may become visible out of order:
+        // whatever lies behind a gap waits for the next turn) ----
+        uint32_t window = 1;
+        if (lane == 0) window = min(32u, max(1u, 2u * max(e.tail_seen, s_ctl[1]) / total_warps));
+        window = __shfl_sync(0xffffffffu, window, 0);
+        const uint64_t slot64 = (uint64_t)gw + (uint64_t)(next + lane) * total_warps;
+        uint4 it = make_uint4(kQEmpty, 0, 0, 0);
+        if (lane < window && slot64 < e.sh.queue_cap) it = ld_rec(e.sh.queue + (uint32_t)slot64);
+        const uint32_t filled = __ballot_sync(0xffffffffu, it.x != kQEmpty);
+        const uint32_t take = filled == 0xffffffffu ? 32u : (uint32_t)__ffs(~filled) - 1u; // >= 1: lane 0 saw its record
+        const bool valid = lane < take;
+        const uint32_t got = take == 32u ? 0xffffffffu : ((1u << take) - 1u);
+        next += take;
+        COL_ADD(10, 1);
+        COL_ADD(11, take);
+        COL_T(t1b);
+        COL_ADD(6, t1b - t1);
+
+        // ---- phase 1: lane l prepares its item ----
+        uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, key = 0;
+        uint64_t ptrA = 0, ptrB = 0;
+        bool work = false;
+        if (valid)
+        {
+            const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
+            const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
+            const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
+            const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
+            const bool root = (it.z | it.w) == 0u;
+            const uint32_t k = root ? levels0 : levels;
+            const uint32_t da = min(k, A.L - la), db = min(k, B.L - lb);
+            const uint32_t lca = la + da, lcb = lb + db;
+            const uint32_t fa = pa << da, fb = pb << db;
+            const uint32_t nA = min(1u << da, va.count(lca) - fa);
+            const uint32_t nB = min(1u << db, vb.count(lcb) - fb);
+            const uint32_t combos = nA * nB; // <= 1024
+            const bool to_cand = (lca == A.L) && (lcb == B.L);
+            work = true;
+            ptrA = (uint64_t)A.nodes;
+            ptrB = (uint64_t)B.nodes;
+            baseA = va.offset(lca) + fa;
+            baseB = vb.offset(lcb) + fb;
+            // Start fetching the two runs of descendant boxes NOW, for all the items of the batch at once (the lanes
+            // set their items up in parallel): phase 2 walks the items one after the other, and without this every
+            // item would wait its own L2 round trip. No register is held.
+            {
+                const char* ra = reinterpret_cast<const char*>(A.nodes) + 24ull * baseA;
+                const char* rb = reinterpret_cast<const char*>(B.nodes) + 24ull * baseB;
+                for (uint32_t o = 0; o < 24u * nA + 127u; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + o));
+                for (uint32_t o = 0; o < 24u * nB + 127u; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + o));
+            }
+            ex = it.x;
+            ey = it.y;
+            // emitted node ids are za + ia / zb + ib (fa, fb have their low da / db bits clear)
+            za = to_cand ? fa : ((lca << kNodeLevelShift) | fa);
+            zb = to_cand ? fb : ((lcb << kNodeLevelShift) | fb);
+            meta = combos | (nB << 11) | (db << 17) | ((nB == (1u << db)) ? 1u << 20 : 0u) | (to_cand ? 1u << 21 : 0u) |
+                   ((root && world > 1) ? 1u << 22 : 0u);
+            // the children of a root pair are dealt round-robin to the shards, keyed by the pair's linear index
+            key = pair_linear(n_obj, it.x, it.y);
+            atomicAdd(s_hist + min(la, 31u), 1u); // items per tree level of side A (oibvh_scene_get_round_stats)
+        }
+        COL_T(t1c);
+        COL_ADD(7, t1c - t1b);
+        // ---- phase 2: the warp walks the prepared items, 64 descendant pairs per step ----
+        for (uint32_t todo = __ballot_sync(0xffffffffu, work); todo; todo &= todo - 1)
+        {
+            const int k = __ffs(todo) - 1;
+            const uint32_t mk = __shfl_sync(0xffffffffu, meta, k);
+            const uint32_t combos = mk & 0x7ffu, nB = (mk >> 11) & 63u, db = (mk >> 17) & 7u;
+            const bool to_cand = (mk >> 21) & 1u, sharded = (mk >> 22) & 1u;
+            const float2* nodesA = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrA, k));
+            const float2* nodesB = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrB, k));
+            const uint32_t bA = __shfl_sync(0xffffffffu, baseA, k), bB = __shfl_sync(0xffffffffu, baseB, k);
+            const uint32_t exk = __shfl_sync(0xffffffffu, ex, k), eyk = __shfl_sync(0xffffffffu, ey, k);
+            const uint32_t zak = __shfl_sync(0xffffffffu, za, k), zbk = __shfl_sync(0xffffffffu, zb, k);
+            const uint32_t kk = __shfl_sync(0xffffffffu, key, k);
+            for (uint32_t g0 = 0; g0 < combos; g0 += 64) // warp-uniform
+            {
+                const uint32_t c0 = g0 + lane, c1 = c0 + 32;
+                bool hit0 = c0 < combos, hit1 = c1 < combos;
+                if (sharded)
+                {
+                    hit0 = hit0 && ((kk + c0) % world) == rank;
+                    hit1 = hit1 && ((kk + c1) % world) == rank;
+                }
+                // nB is a power of two unless the rectangle is clamped by the end of the level (warp-uniform)
+                uint32_t ia0, ib0, ia1, ib1;
+                if ((mk >> 20) & 1u)
+                {
+                    ia0 = c0 >> db;
+                    ib0 = c0 & (nB - 1);
+                    ia1 = c1 >> db;
+                    ib1 = c1 & (nB - 1);
+                }
+                else
+                {
+                    ia0 = c0 / nB;
+                    ib0 = c0 - ia0 * nB;
+                    ia1 = c1 / nB;
+                    ib1 = c1 - ia1 * nB;
+                }
+                Box a0, b0, a1, b1;
+                if (hit0)
+                {
+                    a0 = load_box(nodesA, bA + ia0);
+                    b0 = load_box(nodesB, bB + ib0);
+                }
+                if (hit1)
+                {
+                    a1 = load_box(nodesA, bA + ia1);
+                    b1 = load_box(nodesB, bB + ib1);
+                }
+                if (hit0) hit0 = box_overlap(a0, b0);
+                if (hit1) hit1 = box_overlap(a1, b1);
+                stage_hits(e, lane, to_cand, hit0, hit1, make_uint4(exk, eyk, zak + ia0, zbk + ib0),
+                           make_uint4(exk, eyk, zak + ia1, zbk + ib1));
+            }
+        }
+        // ---- the batch is finished only when everything it produced has left the warp ----
+        COL_T(t3);
+        COL_ADD(2, t3 - t1b);
+        flush_queue(e, lane);
+        COL_T(t4);
+        COL_ADD(3, t4 - t3);
+        if (e.staged_c) COL_ADD(12, 1);
+        flush_candidates(e, lane);
+        COL_T(t5);
+        COL_ADD(4, t5 - t4);
+        if (lane == 0) e.retire += (uint32_t)__popc(got); // retired with the next reservation, or when out of work
+    }
+#ifdef OIBVH_PROFILE
+    if (lane == 0)
+    {
+        prof[5] = (unsigned long long)(clock64() - t_begin);
+        for (int i = 0; i < 16; i++)
+            if (prof[i]) atomicAdd(g_col_prof + i, prof[i]);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -615,14 +853,17 @@ __device__ void narrow_phase(const ObjDesc* s_objs, const ObjDesc* __restrict__ 
 constexpr size_t kColStageBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 128 KB
 constexpr size_t kColSmemBytes = kColStageBytes;
 __global__ void __launch_bounds__(kColThreads, 1)
-    collide_kernel(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* front0, uint4* front1, uint32_t front_cap,
-                   uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap, uint32_t* counters,
-                   uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, const MgpuArgs mg)
+    collide_kernel(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap, uint4* pairs,
+                   uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world,
+                   const MgpuArgs mg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_stage = reinterpret_cast<uint4*>(smem_raw); // kColWarps x kStageCap records
-    __shared__ __align__(16) ObjDesc s_objs[kObjCache];
+    __shared__ __align__(16) EmitShared s_emit;
+    ObjDesc* const s_objs = s_emit.s_objs;
     __shared__ uint32_t s_lv[kObjCache * 64]; // per cached object: off[32], cnt[32]
+    __shared__ uint32_t s_hist[32];           // items per tree level (statistics)
+    __shared__ uint32_t s_ctl[2];             // CTA copy of (stop flag, queue tail), refreshed by one warp at a time
     for (uint32_t i = threadIdx.x; i < min(n_obj, (uint32_t)kObjCache) * 32; i += blockDim.x)
     {
         const uint32_t o = i >> 5, l = i & 31u;
@@ -631,9 +872,23 @@ __global__ void __launch_bounds__(kColThreads, 1)
         s_lv[o * 64 + l] = l <= d.L ? level_offset(d.T, d.L, l) : 0u;
         s_lv[o * 64 + 32 + l] = l <= d.L ? level_count(d.T, d.L, l) : 0u;
     }
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0u;
+    if (threadIdx.x == 0)
+    {
+        s_ctl[0] = s_ctl[1] = 0u;
+        const bool remote = mg.mode == 2;
+        s_emit.queue = queue;
+        s_emit.queue_cap = queue_cap;
+        s_emit.counters = counters;
+        s_emit.objs = objs;
+        s_emit.remote = remote ? 1u : 0u;
+        s_emit.pairs = remote ? mg.root_pairs : pairs;
+        s_emit.pair_cap = remote ? mg.root_pair_cap : pair_cap;
+        s_emit.pair_ctr = remote ? mg.root_counters : counters;
+    }
     // multi-GPU: this launch is frame MG_FRAME + 1 of the scene. A remote rank may append to the root's list only once
     // the root has zeroed its counter block for this frame (MG_OPEN >= frame): one thread per CTA polls the root's word
-    // over NVLink NOW, off the critical path, and the narrow phase picks the answer up from shared memory.
+    // over NVLink NOW, off the critical path; the answer is picked up from shared memory after the seeding.
     __shared__ uint32_t s_mg_ok;
     uint32_t mg_frame = 0;
     if (mg.mode != 0)
@@ -652,59 +907,56 @@ __global__ void __launch_bounds__(kColThreads, 1)
         }
     }
     __syncthreads();
-    uint32_t gen = 0;
+    if (mg.mode == 2 && !s_mg_ok)
+    {
+        // the root never opened this frame: report it, then run to completion without touching its memory
+        if (threadIdx.x == 0)
+        {
+            atomicOr(counters + CTR_OVERFLOW, 16u);
+            s_emit.remote = 0u;
+            s_emit.pairs = pairs;
+            s_emit.pair_cap = 0; // nothing is stored
+            s_emit.pair_ctr = counters;
+        }
+        __syncthreads();
+    }
     uint32_t n_stamps = 0;
-    auto stamp = [&](uint32_t) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < CTR_WORDS - CTR_TIME0)
+    auto stamp = [&]() {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < CTR_WORDS_TIME)
             counters[CTR_TIME0 + n_stamps] = (uint32_t)clock64();
         n_stamps++;
     };
-    stamp(0);
-    // few object pairs (the common two-body scene): round 0 computes the root pairs on the fly, which saves the seeding
-    // pass and its grid barrier; many-body scenes seed the front in parallel first
+    stamp();
+
+    const uint32_t warp = threadIdx.x >> 5;
+    Emit e(s_emit, s_stage + warp * kStageCap);
+
+    // ---- seeds: queue records for the object pairs whose root boxes overlap ----
+    // few pairs (the common two-body scene): every node pair of a deep level tested densely, or the root pairs
+    // themselves; many-body scenes: the tiled top-level pass over the root boxes
     const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
-    const bool computed_seeds = n_pairs <= 4096;
-    uint32_t front_size;
-    if (computed_seeds)
-    {
-        front_size = (uint32_t)n_pairs;
-        if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FRONT0] = front_size;
-    }
+    const bool dense = n_pairs <= 4096 && levels0 > kMaxExpandLevels;
+    if (dense)
+        dense_seed_phase(e, s_lv, (uint32_t)n_pairs, levels0, rank, world, n_obj);
+    else if (n_pairs <= 4096)
+        root_seed_phase(e, s_lv, (uint32_t)n_pairs, n_obj);
     else
-    {
-        seed_phase(reinterpret_cast<float*>(smem_raw), objs, n_obj, front0, front_cap, counters);
-        front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0);
-    }
-    stamp(1);
-    for (uint32_t r = 0; r < rounds && front_size != 0; r++) // front_size is uniform over the grid
-    {
-        uint4* in = (r & 1) ? front1 : front0;
-        uint4* out = (r & 1) ? front0 : front1;
-        if (r == 0 && computed_seeds) in = nullptr;
-        const uint32_t k = r == 0 ? levels0 : levels; // schedule chosen by the host (see scene_enqueue)
-        if (r == 0 && computed_seeds && k > kMaxExpandLevels)
-            dense_seed_phase(s_stage, s_objs, s_lv, objs, out, front_cap, cand, cand_cap, counters, front_size, k, rank,
-                             world, n_obj);
-        else
-            expand_phase(s_stage, s_objs, s_lv, objs, in, out, front_cap, cand, cand_cap, counters, r, front_size, k,
-                         rank, world, n_obj);
-        front_size = grid_barrier(counters, ++gen, counters + CTR_FRONT0 + r + 1);
-        stamp(gen);
-    }
-    const uint32_t n_cand = grid_barrier(counters, ++gen, counters + CTR_CANDIDATES);
-    stamp(gen);
-    if (mg.mode == 2)
-    {
-        if (s_mg_ok)
-            narrow_phase<true>(s_objs, objs, cand, cand_cap, mg.root_pairs, mg.root_pair_cap, counters, n_cand,
-                               mg.root_counters);
-        else if (threadIdx.x == 0)
-            atomicOr(counters + CTR_OVERFLOW, 16u); // the root never opened this frame
-    }
-    else
-        narrow_phase<false>(s_objs, objs, cand, cand_cap, pairs, pair_cap, counters, n_cand, nullptr);
+        seed_phase(reinterpret_cast<float*>(smem_raw), objs, n_obj, queue, queue_cap, counters);
+    const uint32_t seeded = grid_barrier(counters, 1, counters + CTR_Q_TAIL);
+    stamp();
+    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded);
     __syncthreads();
-    stamp(gen + 1);
+    stamp();
+
+    // ---- leave the queue empty for the next launch: every slot that was filled goes back to the empty marker ----
+    // (after the stop flag nobody reads a filled slot any more: they have all been consumed)
+    {
+        const uint32_t filled = min(__ldcg(counters + CTR_Q_TAIL), queue_cap);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < filled; i += gridDim.x * blockDim.x)
+            queue[i] = make_uint4(kQEmpty, kQEmpty, kQEmpty, kQEmpty);
+    }
+    if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(counters + CTR_FRONT0 + threadIdx.x, s_hist[threadIdx.x]);
+    stamp();
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = n_stamps; // number of stamps
     if (mg.mode != 0 && threadIdx.x == 0)
     {
@@ -718,7 +970,9 @@ __global__ void __launch_bounds__(kColThreads, 1)
             st_relaxed_gpu(mg.state + MG_EXIT, 0u);
             st_relaxed_gpu(mg.state + MG_FRAME, mg_frame);
             if (mg.mode == 2)
-                atomicAdd_system(mg.root_state + MG_DONE, 1u);
+            {
+                if (s_mg_ok) atomicAdd_system(mg.root_state + MG_DONE, 1u);
+            }
             else
             {
                 const uint32_t want = (mg.world - 1) * mg_frame;
@@ -854,18 +1108,16 @@ cudaError_t collide_configure(int* grid_blocks)
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    *grid_blocks = sms; // one CTA per SM: the fewest barrier arrivals
+    *grid_blocks = sms; // one CTA per SM
     return cudaSuccess;
 }
 
-cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
-                           uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
-                           uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
-                           uint32_t world, const MgpuArgs& mg, cudaStream_t s)
+cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap,
+                           uint4* pairs, uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels,
+                           uint32_t rank, uint32_t world, const MgpuArgs& mg, cudaStream_t s)
 {
     MgpuArgs mga = mg;
-    void* args[] = {&objs, &n_obj, &front0, &front1, &front_cap, &cand, &cand_cap, &pairs, &pair_cap,
-                    &counters, &rounds, &levels0, &levels, &rank, &world, &mga};
+    void* args[] = {&objs, &n_obj, &queue, &queue_cap, &pairs, &pair_cap, &counters, &levels0, &levels, &rank, &world, &mga};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(collide_kernel), dim3(grid_blocks),
                                        dim3(kColThreads), args, kColSmemBytes, s);
 }

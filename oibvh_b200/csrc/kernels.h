@@ -102,12 +102,18 @@ enum
 {
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
-    CTR_OVERFLOW = 2, // bit 0: front, bit 1: candidates, bit 2: pairs, bit 3: grid barrier timed out, bit 4: multi-GPU wait timed out
+    CTR_OVERFLOW = 2, // bit 0: work queue, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out
     CTR_BARRIER = 3,  // arrival counter of the grid barrier
-    CTR_FRONT0 = 8,   // CTR_FRONT0 + r = size of the front consumed by round r
-    CTR_MAX_ROUNDS = 48,
+    CTR_FRONT0 = 8,   // CTR_FRONT0 + l = BVTT nodes processed whose side-A node is at tree level l (statistics)
+    CTR_MAX_ROUNDS = 32,
     CTR_TIME0 = 64,   // CTR_TIME0 + i = SM cycle counter (low 32 bits) of CTA 0 at phase boundary i
-    CTR_WORDS = 128
+    CTR_WORDS_TIME = 64,
+    // work-queue state, each hot word on a 128-byte line of its own
+    CTR_Q_STATE = 128, // 64-bit: finished items (low half) | pushed records (high half)
+    CTR_Q_TAIL = 129,  // = the high half: pushed records, the next free slot
+    CTR_Q_HEAD = 160,  // claimed slots
+    CTR_Q_STOP = 192,  // traversal finished (or aborted)
+    CTR_WORDS = 256
 };
 
 // ---- multi-GPU detection: replicated BVH, round 0 dealt to `world` ranks, and every rank's narrow phase
@@ -135,14 +141,15 @@ struct MgpuArgs
 // root: zero the counter block of the coming frame, then publish MG_OPEN = frame (system scope)
 cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s);
 
-// Whole detection in one cooperative launch: seeds (one root pair per object pair i<j) -> `rounds` expansion
-// rounds (round 0 descends levels0 levels, the others `levels`; rank/world shard the children of round 0) ->
-// narrow phase. counters must be zeroed before the launch. grid_blocks comes from collide_configure().
+// Whole detection in one cooperative launch: seeds (one root pair per object pair i<j, or every node pair of level
+// levels0 when levels0 > kMaxExpandLevels) -> queue-driven traversal (root pairs descend levels0 levels, the others
+// `levels`; rank/world shard the children of the root pairs) with the narrow phase fused in. `queue` must hold the
+// empty marker (all bits set) in every slot -- the kernel leaves it so --, counters must be zeroed before the launch.
+// grid_blocks comes from collide_configure().
 cudaError_t collide_configure(int* grid_blocks);
-cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* front0, uint4* front1,
-                           uint32_t front_cap, uint4* cand, uint32_t cand_cap, uint4* pairs, uint32_t pair_cap,
-                           uint32_t* counters, uint32_t rounds, uint32_t levels0, uint32_t levels, uint32_t rank,
-                           uint32_t world, const MgpuArgs& mg, cudaStream_t s);
+cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap,
+                           uint4* pairs, uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels,
+                           uint32_t rank, uint32_t world, const MgpuArgs& mg, cudaStream_t s);
 
 // collided-triangle vertex stream (Scene::convertToVertexArray) and node-box wireframes
 // (OibvhTree::convertToVertexArray) as device-side gathers

@@ -32,7 +32,7 @@ def test_bench_line_has_the_contract_keys(ctx):
     assert e["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert 0.05 < r["frac"] < 1.0 and r["traffic"] is None or r["traffic"] > 0
+    assert 0.0 < r["frac"] < 1.0 and (r["traffic"] is None or r["traffic"] > 0)
     c = d["clocks"]
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(c)
     assert d["pairs"] > 0 and d["candidates"] >= d["pairs"]

@@ -1,0 +1,21 @@
+"""Where the detection kernel's warps spend their time (PROFILE variant: make -C oibvh_b200/csrc profile)."""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, bench, oibvh_b200 as ob
+pos, faces = bench.make_meshes()
+mA = ob.Mesh(pos, faces); mB = mA.copy()
+tA = ob.OibvhTree(mA); tA.build()
+tB = ob.OibvhTree(tA, mB)
+M0 = mB.transform_matrix_translate(bench.OFFSET_B); mB.transform(M0); tB.transform(M0); tB.build()
+sc = ob.Scene(); sc.addOibvhTree(tA); sc.addOibvhTree(tB)
+for _ in range(3):
+    sc.detect_async(4, 0); sc.counts()
+buf = np.zeros(16, np.uint64)
+ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
+sc.detect_async(4, 0); print("counts", sc.counts(), "phase cycles", sc.phase_cycles())
+ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 0)
+W = 148 * 32
+names = ["window", "empty polls", "setup+tests", "push", "narrow", "total", "full polls", "setup alone"]
+for i, n in enumerate(names):
+    print(f"  {n:12s} {int(buf[i]) / W:10.0f} cycles per warp")
+print("  empty polls %d  batches %d  items %d  candidate flushes %d" % tuple(int(x) for x in buf[9:13]))
