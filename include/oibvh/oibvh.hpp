@@ -23,6 +23,8 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -166,11 +168,15 @@ inline void check(int rc)
 {
     if (rc != OIBVH_OK) throw std::runtime_error(std::string("oibvh_b200: ") + oibvh_last_error());
 }
-// one context per device, created on first use (the reference uses the current device + default stream)
+// one context per device, created on first use (the reference uses the current device + default stream). The table
+// is guarded by a mutex; a context itself is NOT thread-safe (include/oibvh_b200.h): threads that drive the same
+// device through this facade must serialise their calls, threads on different devices need not.
 inline oibvh_ctx* context(int device = 0)
 {
+    static std::mutex guard;
     static oibvh_ctx* ctx[16] = {nullptr};
     if (device < 0 || device >= 16) throw std::runtime_error("oibvh_b200: bad device index");
+    std::lock_guard<std::mutex> lock(guard);
     if (!ctx[device]) check(oibvh_ctx_create(device, &ctx[device]));
     return ctx[device];
 }
@@ -280,16 +286,42 @@ public:
 
     void build()
     {
+        if (m_static && m_buildDone && !m_dirty) return; // a static tree is built once
         oibvh_detail::check(oibvh_tree_build(m_handle));
         m_buildDone = true;
+        m_dirty = false;
+        m_version++;
     }
     // re-reads the mesh positions like the reference (oibvhTree.cu:196-199)
     void refit()
     {
+        if (m_static && !m_dirty) return; // a static tree is neither re-uploaded nor refitted until markDirty()
         std::vector<float> pos = packedPositions();
         oibvh_detail::check(oibvh_tree_set_positions(m_handle, pos.data()));
         oibvh_detail::check(oibvh_tree_refit(m_handle));
         oibvh_detail::check(oibvh_ctx_synchronize(oibvh_detail::context())); // `pos` is about to go away
+        m_dirty = false;
+        m_version++;
+    }
+    // Extension: the reference re-uploads and refits every tree every frame whether or not its mesh moved
+    // (main.cpp:248-262). A tree marked static keeps what it has: build() and refit() return at once until markDirty()
+    // says the mesh changed (the Mesh members are public, so the facade cannot see a change by itself).
+    void setStatic(bool isStatic)
+    {
+        m_static = isStatic;
+        m_dirty = true; // the next build() / refit() still runs once
+    }
+    void markDirty() { m_dirty = true; }
+    // Extension: Mesh::transform of the vertices ON THE DEVICE followed by the refit, without the host round trip
+    // (same arithmetic, bit-identical positions: oibvh_tree_transform). The host Mesh is transformed too, so both stay
+    // equal like in the reference (src/utils/mesh.cpp:187-213).
+    void transformAndRefitOnDevice(const oibvh_math::mat4& M)
+    {
+        static_assert(sizeof(oibvh_math::mat4) == 64, "mat4 is 16 packed floats, column-major");
+        m_mesh->transform(M);
+        oibvh_detail::check(oibvh_tree_transform(m_handle, reinterpret_cast<const float*>(&M)));
+        oibvh_detail::check(oibvh_tree_refit(m_handle));
+        m_version++;
     }
     unsigned int getDepth() const
     {
@@ -328,13 +360,18 @@ public:
     {
         std::vector<oibvh_tree*> h = handles(trees);
         oibvh_detail::check(oibvh_tree_build_many(h.data(), (uint32_t)h.size()));
-        for (auto& t : trees) t->m_buildDone = true;
+        for (auto& t : trees)
+        {
+            t->m_buildDone = true;
+            t->m_version++;
+        }
     }
     // refit on the positions currently on the device (after transformMany / oibvh_tree_transform)
     static void refitManyOnDevice(const std::vector<std::shared_ptr<OibvhTree>>& trees)
     {
         std::vector<oibvh_tree*> h = handles(trees);
         oibvh_detail::check(oibvh_tree_refit_many(h.data(), (uint32_t)h.size()));
+        for (auto& t : trees) t->m_version++;
     }
     // Mesh::transform of every object on its device-resident vertices, one matrix per tree
     static void transformMany(const std::vector<std::shared_ptr<OibvhTree>>& trees,
@@ -345,6 +382,7 @@ public:
         std::vector<oibvh_tree*> h = handles(trees);
         oibvh_detail::check(oibvh_tree_transform_many(h.data(), (uint32_t)h.size(),
                                                       reinterpret_cast<const float*>(mats.data())));
+        for (auto& t : trees) t->m_version++;
     }
 
     // OibvhTree::convertToVertexArray (src/cuda/oibvhTree.cu:69-124) without the GL upload: wireframe boxes of the
@@ -389,6 +427,8 @@ private:
     }
     std::shared_ptr<Mesh> m_mesh;
     oibvh_tree* m_handle = nullptr;
+    bool m_static = false, m_dirty = true;
+    unsigned long long m_version = 0; // bumped by everything that changes the device tree (replicas follow it)
     friend class Scene;
 };
 
@@ -415,7 +455,15 @@ public:
     Scene() { oibvh_detail::check(oibvh_scene_create(oibvh_detail::context(), &m_handle)); }
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
-    ~Scene() { oibvh_scene_destroy(m_handle); }
+    ~Scene()
+    {
+        for (auto& kv : m_replicas)
+        {
+            oibvh_scene_destroy(kv.second.scene);
+            for (auto* t : kv.second.trees) oibvh_tree_destroy(t);
+        }
+        oibvh_scene_destroy(m_handle);
+    }
 
     void addOibvhTree(std::shared_ptr<OibvhTree> oibvhTree)
     {
@@ -427,14 +475,45 @@ public:
     void detectCollision(const DeviceType deviceType = DeviceType::GPU0, const unsigned int entryLevel = 0,
                          const unsigned int expandLevels = 1)
     {
-        if (deviceType != DeviceType::GPU0)
-            throw std::runtime_error("oibvh_b200: this Scene lives on GPU0 (DeviceType::CPU is a TODO in the reference)");
+        const int dev = static_cast<int>(deviceType);
+        if (dev < 0) throw std::runtime_error("oibvh_b200: DeviceType::CPU is an empty TODO in the reference and there is no CPU path here");
+        // the reference asserts deviceType < m_deviceCount (scene.cu:170)
+        if (dev >= oibvh_device_count()) throw std::runtime_error("oibvh_b200: no such CUDA device");
+        oibvh_scene* scene = m_handle;
+        if (dev != 0)
+        {
+            // GPUk, k > 0: the reference only calls cudaSetDevice(k) and then uses buffers it allocated on another
+            // device (scene.cu:229, 15-21). Here the detection really runs on device k, on replicas of the trees
+            // that are created on first use and refreshed (device-to-device) whenever a tree has changed since.
+            Replica& r = m_replicas[dev];
+            oibvh_ctx* ctx = oibvh_detail::context(dev);
+            if (!r.scene) oibvh_detail::check(oibvh_scene_create(ctx, &r.scene));
+            for (size_t i = 0; i < m_oibvhTrees.size(); i++)
+            {
+                OibvhTree& t = *m_oibvhTrees[i];
+                if (i >= r.trees.size())
+                {
+                    oibvh_tree* rep = nullptr;
+                    oibvh_detail::check(oibvh_tree_replicate(t.m_handle, ctx, &rep));
+                    oibvh_detail::check(oibvh_scene_add_tree(r.scene, rep));
+                    r.trees.push_back(rep);
+                    r.versions.push_back(t.m_version);
+                }
+                else if (r.versions[i] != t.m_version)
+                {
+                    oibvh_detail::check(oibvh_tree_sync_replica(r.trees[i], t.m_handle));
+                    r.versions[i] = t.m_version;
+                }
+            }
+            scene = r.scene;
+        }
         uint32_t n = 0, c = 0;
-        oibvh_detail::check(oibvh_scene_detect(m_handle, entryLevel, expandLevels, &n, &c));
+        oibvh_detail::check(oibvh_scene_detect(scene, entryLevel, expandLevels, &n, &c));
         m_intTriPairCount = n;
         m_candidateCount = c;
         m_intTriPairs.resize(n);
-        oibvh_detail::check(oibvh_scene_get_pairs(m_handle, reinterpret_cast<oibvh_int_tri_pair*>(m_intTriPairs.data())));
+        oibvh_detail::check(oibvh_scene_get_pairs(scene, reinterpret_cast<oibvh_int_tri_pair*>(m_intTriPairs.data())));
+        m_lastScene = scene;
     }
     unsigned int getIntTriPairCount() const { return m_intTriPairCount; }
     unsigned int getCandidateCount() const { return m_candidateCount; } // extension
@@ -444,13 +523,22 @@ public:
     {
         m_vertices.resize((size_t)m_intTriPairCount * 6);
         static_assert(sizeof(oibvh_math::vec3) == 12, "vec3 is three packed floats");
-        oibvh_detail::check(oibvh_scene_pair_vertices(m_handle, reinterpret_cast<float*>(m_vertices.data())));
+        oibvh_detail::check(oibvh_scene_pair_vertices(m_lastScene ? m_lastScene : m_handle,
+                                                      reinterpret_cast<float*>(m_vertices.data())));
     }
     std::vector<oibvh_math::vec3> m_vertices;
 
     std::vector<int_tri_pair_node_t> m_intTriPairs; // {bvhA < bvhB, triA, triB}; tri = Morton-sorted position
 
 private:
+    struct Replica // the scene and its trees on another device (detectCollision(DeviceType::GPUk))
+    {
+        oibvh_scene* scene = nullptr;
+        std::vector<oibvh_tree*> trees;
+        std::vector<unsigned long long> versions;
+    };
+    std::map<int, Replica> m_replicas;
+    oibvh_scene* m_lastScene = nullptr;
     std::vector<std::shared_ptr<OibvhTree>> m_oibvhTrees;
     oibvh_scene* m_handle = nullptr;
     unsigned int m_intTriPairCount = 0;

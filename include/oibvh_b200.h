@@ -102,6 +102,8 @@ int oibvh_ctx_stage_ms(oibvh_ctx* ctx, float ms[OIBVH_STAGE_COUNT]);
  *      allocated); a graph becomes stale -- launch returns OIBVH_ERR_INVALID -- if a work queue is regrown later. */
 int oibvh_ctx_capture_begin(oibvh_ctx* ctx);
 int oibvh_ctx_capture_end(oibvh_ctx* ctx, oibvh_graph** out);
+/* abandon a capture after a failed call (the stream would otherwise stay in capture mode); no graph is produced */
+int oibvh_ctx_capture_abort(oibvh_ctx* ctx);
 int oibvh_graph_launch(oibvh_graph* graph);
 int oibvh_graph_destroy(oibvh_graph* graph);
 
@@ -118,6 +120,14 @@ int oibvh_tree_create_from_device(oibvh_ctx* ctx, const float* dev_positions, ui
 /* OibvhTree(other, mesh) copy constructor (src/cuda/oibvhTree.cu:17-33): same sorted faces / permutation /
  * node array / positions as `other`, sharing nothing on the device. */
 int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out);
+/* A replica of `src` on ANOTHER context / device of this process (the multi-GPU detection keeps every tree on every
+ * GPU; it is also what lets the facade honour Scene::detectCollision(DeviceType::GPUk) for any k,
+ * include/cuda/scene.cuh:12-24): same sorted faces, permutation, positions and node array, copied device to device
+ * (peer copy over NVLink when the devices differ). oibvh_tree_sync_replica refreshes positions and nodes (and the
+ * face order, if `src` has been rebuilt) after `src` changed: cheaper than a refit from host data and bit-identical
+ * by construction. Both calls wait for `src`'s pending work. */
+int oibvh_tree_replicate(const oibvh_tree* src, oibvh_ctx* dst_ctx, oibvh_tree** out);
+int oibvh_tree_sync_replica(oibvh_tree* replica, const oibvh_tree* src);
 int oibvh_tree_destroy(oibvh_tree* tree);
 /* the "copy Mesh positions" head of OibvhTree::refit (src/cuda/oibvhTree.cu:196-199, 208) */
 int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_positions);

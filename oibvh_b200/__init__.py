@@ -62,11 +62,14 @@ _SIGNATURES = {
     "oibvh_ctx_stage_ms": (C.c_int, [_vp, _f32p]),
     "oibvh_ctx_capture_begin": (C.c_int, [_vp]),
     "oibvh_ctx_capture_end": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "oibvh_ctx_capture_abort": (C.c_int, [_vp]),
     "oibvh_graph_launch": (C.c_int, [_vp]),
     "oibvh_graph_destroy": (C.c_int, [_vp]),
     "oibvh_tree_create": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _f32p, C.POINTER(_vp)]),
     "oibvh_tree_create_from_device": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _f32p, C.POINTER(_vp)]),
     "oibvh_tree_clone": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "oibvh_tree_replicate": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "oibvh_tree_sync_replica": (C.c_int, [_vp, _vp]),
     "oibvh_tree_destroy": (C.c_int, [_vp]),
     "oibvh_tree_set_positions": (C.c_int, [_vp, _vp]),
     "oibvh_tree_set_positions_from_device": (C.c_int, [_vp, _vp]),
@@ -237,6 +240,9 @@ class Context:
         _check(_lib.oibvh_ctx_capture_end(self._h, C.byref(g)))
         return Graph(self, g)
 
+    def capture_abort(self):
+        _check(_lib.oibvh_ctx_capture_abort(self._h))
+
 
 class Graph:
     def __init__(self, ctx, h):
@@ -393,6 +399,20 @@ class OibvhTree:
                                           C.byref(h)))
             self._h = h
             self.m_buildDone = False
+
+    def replicate(self, ctx):
+        """a replica of this tree on another context / device of this process (oibvh_tree_replicate)"""
+        t = OibvhTree.__new__(OibvhTree)
+        t.ctx, t.m_mesh, t.m_buildDone = ctx, self.m_mesh, self.m_buildDone
+        h = _vp()
+        _check(_lib.oibvh_tree_replicate(self._h, ctx._h, C.byref(h)))
+        t._h = h
+        return t
+
+    def sync_replica(self, src):
+        """refresh this replica after `src` changed (positions, nodes, face order)"""
+        _check(_lib.oibvh_tree_sync_replica(self._h, src._h))
+        self.m_buildDone = src.m_buildDone
 
     def close(self):
         if getattr(self, "_h", None):

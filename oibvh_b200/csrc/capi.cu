@@ -531,6 +531,20 @@ extern "C" int oibvh_ctx_capture_begin(oibvh_ctx* ctx)
     return OIBVH_OK;
 }
 
+// a call that failed between capture_begin and capture_end leaves the stream in capture mode: abandon the capture
+extern "C" int oibvh_ctx_capture_abort(oibvh_ctx* ctx)
+{
+    REQUIRE(ctx != nullptr, "ctx is NULL");
+    if (!ctx->capturing) return OIBVH_OK;
+    DeviceGuard g(ctx->device);
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaStreamEndCapture(ctx->stream, &graph); // an invalidated capture returns an error and a null graph
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return OIBVH_OK;
+}
+
 extern "C" int oibvh_ctx_capture_end(oibvh_ctx* ctx, oibvh_graph** out)
 {
     REQUIRE(ctx && out, "NULL argument");
@@ -690,11 +704,84 @@ extern "C" int oibvh_tree_clone(const oibvh_tree* other, oibvh_tree** out)
     return OIBVH_OK;
 }
 
+// device-to-device copy of everything a built tree consists of, from src's device to dst's, on dst's stream
+static int tree_copy_state(oibvh_tree* dst, const oibvh_tree* src, bool with_faces)
+{
+    oibvh_ctx* dc = dst->ctx;
+    const oibvh_ctx* sc = src->ctx;
+    const size_t T = src->T;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](void* d, const void* s, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = dc->device == sc->device ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, dc->stream)
+                                     : cudaMemcpyPeerAsync(d, dc->device, s, sc->device, bytes, dc->stream);
+    };
+    cp(dst->pos, src->pos, sizeof(float4) * (size_t)src->V);
+    if (with_faces) cp(dst->faces_in, src->faces_in, sizeof(uint4) * T);
+    if (src->built)
+    {
+        cp(dst->nodes, src->nodes, sizeof(float) * 6 * (size_t)src->N);
+        if (with_faces)
+        {
+            cp(dst->faces, src->faces, sizeof(uint32_t) * 3 * T);
+            cp(dst->keys_a, src->keys_a, sizeof(uint32_t) * T);
+            cp(dst->vals_a, src->vals_a, sizeof(uint32_t) * T);
+        }
+    }
+    if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "replica copy failed: %s", cudaGetErrorString(e));
+    dst->built = src->built;
+    dst->upload_pending = false;
+    dst->epoch++;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_replicate(const oibvh_tree* src, oibvh_ctx* dst_ctx, oibvh_tree** out)
+{
+    REQUIRE(src && dst_ctx && out, "NULL argument");
+    *out = nullptr;
+    REQUIRE(!dst_ctx->capturing && !src->ctx->capturing, "replicate outside a graph capture");
+    {
+        DeviceGuard gs(src->ctx->device);
+        int rc = tree_flush_upload(const_cast<oibvh_tree*>(src));
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(src->ctx->stream)); // src's pending builds / refits have produced what is copied
+    }
+    DeviceGuard g(dst_ctx->device);
+    oibvh_tree* t = nullptr;
+    int rc = tree_alloc(dst_ctx, src->V, src->T, src->mesh.v, &t);
+    if (rc) return rc;
+    rc = tree_copy_state(t, src, true);
+    if (rc)
+    {
+        tree_free(t);
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_tree_sync_replica(oibvh_tree* replica, const oibvh_tree* src)
+{
+    REQUIRE(replica && src, "NULL argument");
+    REQUIRE(replica->T == src->T && replica->V == src->V, "not a replica of this tree (sizes differ)");
+    REQUIRE(!replica->ctx->capturing && !src->ctx->capturing, "sync outside a graph capture");
+    {
+        DeviceGuard gs(src->ctx->device);
+        int rc = tree_flush_upload(const_cast<oibvh_tree*>(src));
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(src->ctx->stream));
+    }
+    DeviceGuard g(replica->ctx->device);
+    return tree_copy_state(replica, src, true);
+}
+
 extern "C" int oibvh_tree_destroy(oibvh_tree* tree)
 {
     if (!tree) return OIBVH_OK;
     DeviceGuard g(tree->ctx->device);
     cudaStreamSynchronize(tree->ctx->stream);
+    tree->ctx->generation++; // graphs that captured this tree's buffers must not replay
     tree->ctx->small_table.key.clear(); // cached *_many tables may name this tree
     tree->ctx->xform_table.key.clear();
     tree_free(tree);
@@ -710,7 +797,9 @@ extern "C" int oibvh_tree_set_positions(oibvh_tree* tree, const float* host_posi
     const size_t bytes = sizeof(float) * 3 * (size_t)tree->V;
     if (ctx->capturing)
     {
-        // inside a graph capture everything stays on the one captured stream
+        // inside a graph capture everything stays on the one captured stream. The memcpy node keeps the CALLER'S
+        // pointer: every replay reads host_positions again, so the buffer must outlive the graph (documented in the
+        // header); use oibvh_tree_set_positions_from_device for data that is produced per frame.
         CU(cudaMemcpyAsync(tree->pos_stage, host_positions, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     else
@@ -1145,6 +1234,8 @@ static int transform_many_impl(oibvh_tree* const* trees, uint32_t n, const float
             CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mats), bytes));
             ctx->d_mats_cap = bytes;
         }
+        // (a captured graph would re-read the caller's host array on every replay, and callers pass temporaries)
+        REQUIRE(!ctx->capturing, "host matrices cannot be captured into a graph: use oibvh_tree_transform_many_from_device");
         CU(cudaMemcpyAsync(ctx->d_mats, mats, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_mats = ctx->d_mats;
     }

@@ -170,3 +170,19 @@ def test_two_processes_cuda_ipc(port):
         if p.is_alive():
             p.kill()
     assert p.exitcode == 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cpp_host_threads_drive_the_mgpu_abi(world):
+    """tests/cpp/mgpu_threads: one C++ host thread per rank through the C ABI (replicated trees, peer-mapped pair list,
+    frames without host synchronisation between the ranks). With more ranks than devices (a single-GPU box) the ranks
+    share a device and the test orders the frames on the host with oibvh_mgpu_open_frame."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "mgpu_threads")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "cpp")])
+    res = subprocess.run([exe, str(world), "6"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    first = res.stdout.splitlines()[0].split()
+    assert first[:5] == ["ok", "ranks", str(world), "frames", "6"] and int(first[6]) > 0, res.stdout
