@@ -149,6 +149,12 @@ int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n);
 int oibvh_tree_refit(oibvh_tree* tree);
 /* the per-object refit loop of a many-body frame: small trees in one launch, larger ones one launch each */
 int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n);
+/* Rigid transform + refit of several trees in one call: host_mats = n x 16 floats (column-major), apply[i] != 0 selects
+ * the trees that are transformed (NULL = all); every tree is then refitted. The transform of one tree runs under the
+ * refit of another (two streams) instead of in front of both; capturable with host matrices (they travel as kernel
+ * arguments). Same arithmetic and bits as oibvh_tree_transform followed by oibvh_tree_refit_many. */
+int oibvh_tree_transform_refit_many(oibvh_tree* const* trees, uint32_t n, const float* host_mats,
+                                    const unsigned char* apply);
 /* oibvh_tree_transform for n trees in one launch; mats = n column-major 4x4 matrices (host / device memory) */
 int oibvh_tree_transform_many(oibvh_tree* const* trees, uint32_t n, const float* host_mats);
 int oibvh_tree_transform_many_from_device(oibvh_tree* const* trees, uint32_t n, const float* dev_mats);

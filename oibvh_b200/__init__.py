@@ -77,6 +77,7 @@ _SIGNATURES = {
     "oibvh_tree_build": (C.c_int, [_vp]),
     "oibvh_tree_build_many": (C.c_int, [C.POINTER(_vp), _u32]),
     "oibvh_tree_refit_many": (C.c_int, [C.POINTER(_vp), _u32]),
+    "oibvh_tree_transform_refit_many": (C.c_int, [C.POINTER(_vp), _u32, _f32p, C.c_char_p]),
     "oibvh_tree_transform_many": (C.c_int, [C.POINTER(_vp), _u32, _f32p]),
     "oibvh_tree_transform_many_from_device": (C.c_int, [C.POINTER(_vp), _u32, _vp]),
     "oibvh_tree_refit": (C.c_int, [_vp]),
@@ -553,6 +554,16 @@ def build_many(trees):
 def refit_many(trees):
     """refit several trees on their device-resident positions (oibvh_tree_refit_many): small trees in one launch"""
     _check(_lib.oibvh_tree_refit_many(_handles(trees), len(trees)))
+
+
+def transform_refit_many(trees, mats, apply=None):
+    """Mesh::transform of the selected trees followed by the refit of ALL of them, in one call: the transform of one
+    body overlaps the refit of another (oibvh_tree_transform_refit_many). mats: [n, 4, 4] or [n, 16] column-major
+    (row i is ignored when apply[i] is false)."""
+    h, n = _handles(trees), len(trees)
+    m = np.ascontiguousarray(np.asarray(mats, np.float32).reshape(n, 16))
+    flags = None if apply is None else bytes(bytearray(1 if a else 0 for a in apply))
+    _check(_lib.oibvh_tree_transform_refit_many(h, n, m.ctypes.data_as(_f32p), flags))
 
 
 def transform_many(trees, mats, device_ptr=None):

@@ -90,6 +90,9 @@ struct oibvh_ctx
     // control blocks of the cooperative sort (kMaxLsdJobs jobs per launch). One set per context: the sorts of a
     // context are ordered on `stream`, and every launch leaves the blocks re-armed.
     uint32_t* lsd_ctl = nullptr;
+    // device status word the build kernels OR their bounded-wait failures into (bit 0: sort barrier, bit 1: emit
+    // finisher); checked by oibvh_ctx_synchronize and oibvh_tree_download
+    uint32_t* d_status = nullptr;
 };
 
 struct oibvh_graph
@@ -363,6 +366,19 @@ uint32_t grow_to(uint32_t cap, uint64_t needed)
 
 } // namespace
 
+// the stream has been synchronised: did a build kernel give up a bounded wait since the last check?
+static int ctx_check_status(oibvh_ctx* ctx)
+{
+    uint32_t st = 0;
+    CU(cudaMemcpy(&st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st == 0) return OIBVH_OK;
+    cudaMemset(ctx->d_status, 0, sizeof(st));
+    if (ctx->lsd_ctl) cudaMemset(ctx->lsd_ctl, 0, sizeof(uint32_t) * kMaxLsdJobs * lsd_sort_ctl_words());
+    return fail(OIBVH_ERR_INTERNAL, "a build kernel timed out waiting for other thread blocks (%s%s): the trees built or "
+                                    "refitted since the last check are invalid -- rebuild them",
+                (st & 1u) ? "radix sort barrier " : "", (st & 2u) ? "top-of-tree reduction" : "");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------------------------------
@@ -423,6 +439,8 @@ static int ctx_create_impl(int device, void* stream, bool use_given, oibvh_ctx**
     if (e == cudaSuccess) e = lsd_sort_configure();
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->lsd_ctl), sizeof(uint32_t) * kMaxLsdJobs * lsd_sort_ctl_words());
     if (e == cudaSuccess) e = cudaMemset(c->lsd_ctl, 0, sizeof(uint32_t) * kMaxLsdJobs * lsd_sort_ctl_words());
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_status), 64);
+    if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, 64);
     if (e == cudaSuccess) e = small_trees_configure();
     if (e != cudaSuccess)
     {
@@ -468,6 +486,7 @@ extern "C" int oibvh_ctx_destroy(oibvh_ctx* ctx)
     cudaFree(ctx->xform_table.dev);
     cudaFree(ctx->d_mats);
     cudaFree(ctx->lsd_ctl);
+    cudaFree(ctx->d_status);
     delete ctx;
     return OIBVH_OK;
 }
@@ -477,7 +496,7 @@ extern "C" int oibvh_ctx_synchronize(oibvh_ctx* ctx)
     REQUIRE(ctx != nullptr, "ctx is NULL");
     DeviceGuard g(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    return OIBVH_OK;
+    return ctx_check_status(ctx);
 }
 
 extern "C" int oibvh_ctx_get_stream(oibvh_ctx* ctx, void** cuda_stream)
@@ -886,7 +905,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
             count_launch(ctx);
         }
         StageScope ss(ctx, OIBVH_STAGE_SORT);
-        CU(launch_lsd_sort_many(1, &tree->keys_a, &tree->vals_a, &tree->sort_rec, &tree->T, ctx->lsd_ctl, s));
+        CU(launch_lsd_sort_many(1, &tree->keys_a, &tree->vals_a, &tree->sort_rec, &tree->T, ctx->lsd_ctl, ctx->d_status, s));
         count_launch(ctx);
     }
     else
@@ -916,7 +935,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     static_assert(kRadixPasses % 2 == 0, "an even number of passes leaves the result in (keys_a, vals_a)");
     StageScope se(ctx, OIBVH_STAGE_EMIT);
     CU(launch_tree_emit(true, tree->faces_in, tree->vals_a, tree->faces, tree->pos, tree->nodes, tree->T,
-                        tree->done_counter, s));
+                        tree->done_counter, ctx->d_status, s));
     count_launch(ctx);
     tree->built = true;
     tree->epoch++;
@@ -1059,7 +1078,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     sub.reset(); // records the end of the key kernels before the next scope opens
     sub.reset(new StageScope(ctx, OIBVH_STAGE_SORT));
-    const cudaError_t e = launch_lsd_sort_many(n, ka, va, rec, T, ctx->lsd_ctl, s);
+    const cudaError_t e = launch_lsd_sort_many(n, ka, va, rec, T, ctx->lsd_ctl, ctx->d_status, s);
     if (e == cudaErrorInvalidValue)
     {
         // very unequal sizes (a tree would need more than kLsdKMulti keys per thread of its CTA share): sort one by one
@@ -1067,7 +1086,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
         for (uint32_t i = 0; i < n; i++)
         {
             oibvh_tree* t = trees[i];
-            CU(launch_lsd_sort_many(1, &t->keys_a, &t->vals_a, &t->sort_rec, &t->T, ctx->lsd_ctl, s));
+            CU(launch_lsd_sort_many(1, &t->keys_a, &t->vals_a, &t->sort_rec, &t->T, ctx->lsd_ctl, ctx->d_status, s));
             count_launch(ctx);
         }
     }
@@ -1085,7 +1104,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
     for (uint32_t i = 0; i < n; i++)
     {
         oibvh_tree* t = trees[i];
-        CU(launch_tree_emit(true, t->faces_in, t->vals_a, t->faces, t->pos, t->nodes, t->T, t->done_counter,
+        CU(launch_tree_emit(true, t->faces_in, t->vals_a, t->faces, t->pos, t->nodes, t->T, t->done_counter, ctx->d_status,
                             (i & 1) ? ctx->aux_stream : s));
         count_launch(ctx);
         t->built = true;
@@ -1110,7 +1129,7 @@ extern "C" int oibvh_tree_refit(oibvh_tree* tree)
     if (tree->small)
         CU(launch_small_trees(false, tree->d_small, 0, 1, ctx->stream));
     else
-        CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter,
+        CU(launch_tree_emit(false, nullptr, nullptr, tree->faces, tree->pos, tree->nodes, tree->T, tree->done_counter, ctx->d_status,
                             ctx->stream));
     count_launch(ctx);
     tree->epoch++;
@@ -1171,7 +1190,69 @@ extern "C" int oibvh_tree_refit_many(oibvh_tree* const* trees, uint32_t n)
         if (t->small)
             CU(launch_small_trees(false, t->d_small, 0, 1, st));
         else
-            CU(launch_tree_emit(false, nullptr, nullptr, t->faces, t->pos, t->nodes, t->T, t->done_counter, st));
+            CU(launch_tree_emit(false, nullptr, nullptr, t->faces, t->pos, t->nodes, t->T, t->done_counter, ctx->d_status, st));
+        count_launch(ctx);
+        t->epoch++;
+    }
+    CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return OIBVH_OK;
+}
+
+// Rigid transform + refit of several trees in one call (the transform belongs to the refit). Per tree
+// the two launches are ordered on ONE stream and independent trees alternate between the context's two streams, so
+// the transform of one body runs under the refit of another instead of in front of both (in the two-body frame: the
+// 6 us transform of B disappears under the refit of A). Matrices travel as kernel arguments, so the call can be
+// captured into a graph with host matrices. Same kernels, same bits as oibvh_tree_transform + oibvh_tree_refit.
+extern "C" int oibvh_tree_transform_refit_many(oibvh_tree* const* trees, uint32_t n, const float* host_mats,
+                                               const unsigned char* apply)
+{
+    REQUIRE(trees != nullptr && n >= 1, "no trees");
+    REQUIRE(host_mats != nullptr || apply != nullptr, "matrices are NULL");
+    oibvh_ctx* ctx = trees[0] ? trees[0]->ctx : nullptr;
+    bool any_small = false;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        REQUIRE(trees[i] != nullptr, "NULL tree");
+        REQUIRE(trees[i]->ctx == ctx, "trees belong to different contexts");
+        REQUIRE(trees[i]->built, "refit before build");
+        REQUIRE(!(apply && apply[i]) || host_mats != nullptr, "a tree is to be transformed but the matrices are NULL");
+        any_small = any_small || trees[i]->small;
+    }
+    if (any_small || n < 2)
+    {
+        // many-body scenes go through the batched launches (one transform launch, one refit launch for all)
+        for (uint32_t i = 0; i < n; i++)
+            if (!apply || apply[i])
+            {
+                int rc = oibvh_tree_transform(trees[i], host_mats + 16 * (size_t)i);
+                if (rc) return rc;
+            }
+        return oibvh_tree_refit_many(trees, n);
+    }
+    DeviceGuard g(ctx->device);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        int rc = tree_flush_upload(trees[i]);
+        if (rc) return rc;
+    }
+    StageScope scope(ctx, OIBVH_STAGE_REFIT); // (the transforms are inside: they overlap the other trees' refits)
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    // trees WITH a transform first on the auxiliary stream so that the longer chains start first
+    for (uint32_t i = 0; i < n; i++)
+    {
+        oibvh_tree* t = trees[i];
+        const bool xf = !apply || apply[i];
+        cudaStream_t st = (i & 1) ? ctx->aux_stream : ctx->stream;
+        if (xf)
+        {
+            Mat4 m;
+            memcpy(m.m, host_mats + 16 * (size_t)i, sizeof(float) * 16);
+            CU(launch_transform(t->pos, t->V, m, st));
+            count_launch(ctx);
+        }
+        CU(launch_tree_emit(false, nullptr, nullptr, t->faces, t->pos, t->nodes, t->T, t->done_counter, ctx->d_status, st));
         count_launch(ctx);
         t->epoch++;
     }
@@ -1297,7 +1378,7 @@ extern "C" int oibvh_tree_download(oibvh_tree* tree, oibvh_aabb* host_nodes, uin
         CU(cudaMemcpyAsync(host_perm, tree->vals_a, sizeof(uint32_t) * (size_t)tree->T, cudaMemcpyDeviceToHost,
                            ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return OIBVH_OK;
+    return ctx_check_status(ctx);
 }
 
 extern "C" int oibvh_tree_download_positions(oibvh_tree* tree, float* host_positions)

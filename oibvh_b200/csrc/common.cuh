@@ -203,7 +203,7 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t generation
         {
             if (++spins > (1u << 26))
             {
-                atomicOr(fail_flag, 1u);
+                atomicOr(fail_flag, 1u); // surfaced by the host (oibvh_ctx_synchronize / downloads / scene_add_tree)
                 break;
             }
         }

@@ -39,13 +39,16 @@ cudaError_t lsd_sort_configure();
 uint32_t lsd_sort_capacity();
 uint32_t lsd_sort_capacity_multi();
 size_t lsd_sort_ctl_words();
+// status: the context's device status word (bit 0 = a grid barrier of the sort timed out: the order is invalid)
 cudaError_t launch_lsd_sort_many(uint32_t n, uint32_t* const* keys, uint32_t* const* vals, uint2* const* rec,
-                                 const uint32_t* T, uint32_t* ctl, cudaStream_t s);
+                                 const uint32_t* T, uint32_t* ctl, uint32_t* status, cudaStream_t s);
 cudaError_t tree_emit_configure();
 // arrival counters of the hierarchical top-of-tree completion (zeroed once; the kernel re-arms them)
 size_t emit_counter_words(uint32_t T);
+// status: the context's device status word (bit 1 = the finisher gave up waiting for a chunk)
 cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
-                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s);
+                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, uint32_t* status,
+                             cudaStream_t s);
 cudaError_t launch_transform(float4* pos4, uint32_t V, const Mat4& M, cudaStream_t s);
 
 // ---- many small trees per launch (many-body scenes) ----

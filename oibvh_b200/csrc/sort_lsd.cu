@@ -38,7 +38,6 @@ constexpr int kLsdKMulti = 14;  // several trees side by side: fewer CTAs each, 
 constexpr int kLsdMaxRadix = 1024;
 constexpr size_t kLsdCtlBarrier = 0;  // arrival counter of this job's barriers (own 128-byte line)
 constexpr size_t kLsdCtlExit = 32;    // exit counter: the last CTA to leave re-arms the block for the next launch
-constexpr size_t kLsdCtlFail = 33;    // sticky: a barrier timed out (result invalid); read back by the host
 constexpr size_t kLsdCtlTotals = 64;  // [radix] digit totals of the current pass
 constexpr size_t kLsdCtlCounts = kLsdCtlTotals + kLsdMaxRadix;                          // u16 [radix][pitch]
 constexpr size_t kLsdCtlPrefix = kLsdCtlCounts + (size_t)kLsdMaxRadix * kLsdRowPitch / 2; // u32 [cta][radix]
@@ -56,6 +55,7 @@ struct LsdJobs
 {
     LsdJob j[kMaxLsdJobs];
     uint32_t n;
+    uint32_t* status; // the context's device status word: bit 0 = a barrier timed out (read back by the host)
 };
 
 #ifdef OIBVH_PROFILE
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kLsdThreads, 2) lsd_sort_kernel(const LsdJobs 
         }
         LSD_STAMP(3);
         LSD_BAR(0, 0);
-        grid_sync(ctl + kLsdCtlBarrier, ++gen, ctl + kLsdCtlFail, G);
+        grid_sync(ctl + kLsdCtlBarrier, ++gen, jobs.status, G);
         LSD_BAR(0, 1);
         LSD_STAMP(4);
 
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kLsdThreads, 2) lsd_sort_kernel(const LsdJobs 
         }
         LSD_STAMP(5);
         LSD_BAR(1, 0);
-        grid_sync(ctl + kLsdCtlBarrier, ++gen, ctl + kLsdCtlFail, G);
+        grid_sync(ctl + kLsdCtlBarrier, ++gen, jobs.status, G);
         LSD_BAR(1, 1);
         LSD_STAMP(6);
         if (last && tid == 0)
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kLsdThreads, 2) lsd_sort_kernel(const LsdJobs 
         }
         LSD_STAMP(8);
         LSD_BAR(2, 0);
-        if (!last) grid_sync(ctl + kLsdCtlBarrier, ++gen, ctl + kLsdCtlFail, G);
+        if (!last) grid_sync(ctl + kLsdCtlBarrier, ++gen, jobs.status, G);
         LSD_BAR(2, 1);
         LSD_STAMP(9);
         rin = rout;
@@ -392,7 +392,9 @@ __global__ void __launch_bounds__(kLsdThreads, 2) lsd_sort_kernel(const LsdJobs 
 // ---------------------------------------------------------------------------------------------------------------
 static int g_lsd_grid = 0;
 constexpr int kLsdBits = 10; // measured on B200 (two 2^20-key sorts side by side): 3 x 10 bits 76 us, 4 x 8 bits 85 us,
-                             // 10 bits ranked with match.any 91 us, the round-1 kernel (4 x 8 bits, atomicOr ranking) 87 us
+                             // 10 bits ranked with match.any 91 us, the round-1 kernel (4 x 8 bits, atomicOr ranking) 87 us;
+                             // starting the second job 3-6 us late (so that the two CTAs of an SM are in different
+                             // phases) cost 7 us
 
 template <int K>
 static cudaError_t lsd_configure_one(int* per_sm)
@@ -432,12 +434,13 @@ size_t lsd_sort_ctl_words() { return kLsdCtlWords; }
 // proportion to the sizes. ctl = n consecutive control blocks of lsd_sort_ctl_words() words, zeroed once when
 // allocated (the kernel re-arms them). Returns cudaErrorInvalidValue when the arrays do not fit one wave.
 cudaError_t launch_lsd_sort_many(uint32_t n, uint32_t* const* keys, uint32_t* const* vals, uint2* const* rec,
-                                 const uint32_t* T, uint32_t* ctl, cudaStream_t s)
+                                 const uint32_t* T, uint32_t* ctl, uint32_t* status, cudaStream_t s)
 {
     if (n == 0 || n > (uint32_t)kMaxLsdJobs || g_lsd_grid == 0) return cudaErrorInvalidValue;
     const uint32_t G = (uint32_t)g_lsd_grid;
     LsdJobs jobs;
     jobs.n = n;
+    jobs.status = status;
     uint64_t total = 0;
     for (uint32_t i = 0; i < n; i++) total += T[i];
     if (total == 0) return cudaErrorInvalidValue;

@@ -701,7 +701,8 @@ __device__ __forceinline__ Box emit_warp(const uint4* __restrict__ faces_in4, co
 // launch ended 4.5 us after the last chunk (two dependent fence/atomic/load stages).
 constexpr uint32_t kFinisherSmemNodes = 512; // stage results handed to the next stage through shared memory
 __device__ __noinline__ void emit_finisher(float2* __restrict__ nodes, uint32_t L, const LevelTable& lv, uint32_t* ctr,
-                                              float2* scratch /* the CTA's (otherwise unused) staging area */)
+                                              float2* scratch /* the CTA's (otherwise unused) staging area */,
+                                              uint32_t* status)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint32_t level = L - kChunkLevels; // level of the completed nodes that feed this stage
@@ -725,7 +726,14 @@ __device__ __noinline__ void emit_finisher(float2* __restrict__ nodes, uint32_t 
                 {
                     uint32_t spins = 0;
                     while (ld_acquire_gpu(ctr + g) < members)
-                        if (++spins > (1u << 25)) __trap(); // a chunk CTA never arrived: fail the launch loudly
+                        if (++spins > (1u << 25))
+                        {
+                            // a chunk CTA never arrived: report it through the context's status word (the host turns
+                            // it into an error at the next download / synchronize) instead of trapping, which would
+                            // poison the whole CUDA context of the process
+                            atomicOr(status, 2u);
+                            break;
+                        }
                     ctr[g] = 0; // every member has arrived: re-arm for the next launch on this tree
                 }
                 __syncwarp();
@@ -787,7 +795,7 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
                      const uint32_t* __restrict__ perm,       // BUILD: sorted position -> input face id
                      uint32_t* __restrict__ faces_sorted,     // BUILD: output ; else: input (packed triples)
                      const float4* __restrict__ pos4, float2* __restrict__ nodes, uint32_t T, uint32_t L,
-                     const __grid_constant__ LevelTable lv, uint32_t* done_counter)
+                     const __grid_constant__ LevelTable lv, uint32_t* done_counter, uint32_t* status)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
@@ -801,7 +809,7 @@ __global__ void __launch_bounds__(kEmitThreads, BUILD ? OIBVH_EMIT_MINB_BUILD : 
     const uint32_t has_finisher = gridDim.x * (uint32_t)kChunk >= T + (uint32_t)kChunk ? 1u : 0u;
     if (has_finisher && blockIdx.x == 0)
     {
-        emit_finisher(nodes, L, lv, done_counter, sm);
+        emit_finisher(nodes, L, lv, done_counter, sm, status);
         EMIT_STAMP(3, tid == 0);
         return;
     }
@@ -1289,7 +1297,8 @@ size_t emit_counter_words(uint32_t T)
 }
 
 cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t* perm, uint32_t* faces_sorted,
-                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, cudaStream_t s)
+                             const float4* pos4, float* nodes, uint32_t T, uint32_t* done_counter, uint32_t* status,
+                             cudaStream_t s)
 {
     const uint32_t L = ceil_log2_u32(T);
     uint32_t chunks = (T + kChunk - 1) / kChunk;
@@ -1303,10 +1312,10 @@ cudaError_t launch_tree_emit(bool build, const uint4* faces_in4, const uint32_t*
     }
     if (build)
         tree_emit_kernel<true><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            faces_in4, perm, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter);
+            faces_in4, perm, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter, status);
     else
         tree_emit_kernel<false><<<chunks, kEmitThreads, kEmitSmemBytes, s>>>(
-            nullptr, nullptr, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter);
+            nullptr, nullptr, faces_sorted, pos4, reinterpret_cast<float2*>(nodes), T, L, lv, done_counter, status);
     return cudaGetLastError();
 }
 

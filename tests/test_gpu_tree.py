@@ -113,6 +113,37 @@ def test_device_transform_matches_oracle(ctx, port, golden):
     assert_bit_equal(tree.m_aabbTree, port.refit(g[f"pos{i}"], want["faces"]), "refit on device-resident positions")
 
 
+def test_transform_refit_many_equals_separate_calls(ctx, port):
+    """oibvh_tree_transform_refit_many (transform of one tree under the refit of another, two streams) == transform then
+    refit, tree by tree, bit for bit; also captured into a graph with host matrices"""
+    specs = [meshgen.blob(120, 90, seed=31), meshgen.blob(100, 80, seed=32), meshgen.icosphere(5)]
+    trees, meshes = [], []
+    for pos, faces in specs:
+        m = ob.Mesh(pos, meshgen.shuffle_faces(faces))
+        t = ob.OibvhTree(m, ctx=ctx)
+        t.build()
+        trees.append(t)
+        meshes.append(m)
+    mats = np.stack([m.transform_matrix_rotate((0.2, 1.0, -0.4), 3.0 + i) for i, m in enumerate(meshes)])
+    apply = [True, False, True]
+    want_pos = [port.transform_positions(m.m_positions, M) if a else m.m_positions for m, M, a in zip(meshes, mats, apply)]
+    ob.transform_refit_many(trees, mats, apply)
+    for t, p in zip(trees, want_pos):
+        d = t.download()
+        assert_bit_equal(t.m_positions, p, "positions")
+        assert_bit_equal(d["nodes"], port.refit(p, d["faces"]), "nodes")
+    ctx.capture_begin()
+    ob.transform_refit_many(trees, mats, apply)
+    g = ctx.capture_end()
+    g.launch()
+    ctx.synchronize()
+    g.close()
+    for t, p, M, a in zip(trees, want_pos, mats, apply):
+        p2 = port.transform_positions(p, M) if a else p  # capturing records, the one replay executes
+        assert_bit_equal(t.m_positions, p2, "positions after the replay")
+        assert_bit_equal(t.download()["nodes"], port.refit(p2, t.download()["faces"]), "nodes after the replay")
+
+
 def test_golden_trees_on_gpu(ctx, golden):
     """node arrays frozen from the reference's SimpleBVH: refit over the SAME face order must reproduce them"""
     g = golden["trees"]

@@ -27,7 +27,7 @@ R = mB.transform_matrix_rotate((0, 0, 1), 1.0)
 tB.build()
 sc = ob.Scene(ctx); sc.addOibvhTree(tA); sc.addOibvhTree(tB)
 def frame():
-    ob.build_many([tA, tB]); tB.transform(R); ob.refit_many([tA, tB])
+    ob.build_many([tA, tB]); ob.transform_refit_many([tA, tB], np.stack([ob.mat_identity(), R]), [False, True])
     sc.detect_async(a.entry, a.expand)
 for _ in range(3):
     frame(); sc.counts()
