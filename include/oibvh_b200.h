@@ -181,6 +181,20 @@ int oibvh_scene_destroy(oibvh_scene* scene);
 int oibvh_scene_add_tree(oibvh_scene* scene, oibvh_tree* tree);
 /* restrict this scene to shard `rank` of `world` (seed BVTT nodes are dealt round-robin); default 0 of 1 */
 int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world);
+/* ---- opt-in extensions beyond the reference's behaviour ----------------------------------
+ * Self-collision: the reference only tests object pairs i < j (src/cuda/scene.cu:192-223). With it enabled every
+ * object is also tested against itself: records (i, i, triA, triB) with triA < triB for the intersecting triangle
+ * pairs of object i that share NO vertex index (triangles with a common vertex always touch there: neighbours, not
+ * collisions). Same overlap and SAT rules as between objects.
+ * Temporal coherence: the reference restarts the traversal from entryLevel on every detectCollision
+ * (src/cuda/scene.cu:236). A coherent scene records, during one detection, a complete cut of the BVTT `cut_depth`
+ * levels above the leaves (0 = default 6) and starts the following detections from it, as long as the trees are only
+ * refitted / transformed (any build, added tree or changed shard records a new cut). The pair set is exactly that of
+ * a detection from the roots, for any motion; the cut buffer is sized by `candidate_records` of oibvh_scene_reserve.
+ * Scenes of more than 4096 object pairs ignore the setting. */
+int oibvh_scene_set_self_collision(oibvh_scene* scene, int enable);
+int oibvh_scene_set_coherence(oibvh_scene* scene, int enable, uint32_t cut_depth);
+
 /* size the work queues up front (records): BVTT front (x2), candidate list, pair list. Queues otherwise start at
  * 2^20 / 2^20 / 2^19 records and are regrown after an overflow; a multi-GPU scene cannot regrow (its pair list is
  * mapped by the other ranks), so reserve before oibvh_mgpu_export. Synchronises; invalidates captured graphs. */

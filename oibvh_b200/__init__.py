@@ -92,6 +92,8 @@ _SIGNATURES = {
     "oibvh_scene_add_tree": (C.c_int, [_vp, _vp]),
     "oibvh_scene_set_shard": (C.c_int, [_vp, _u32, _u32]),
     "oibvh_scene_reserve": (C.c_int, [_vp, _u32, _u32, _u32]),
+    "oibvh_scene_set_self_collision": (C.c_int, [_vp, C.c_int]),
+    "oibvh_scene_set_coherence": (C.c_int, [_vp, C.c_int, _u32]),
     "oibvh_mgpu_export": (C.c_int, [_vp, _vp]),
     "oibvh_mgpu_attach": (C.c_int, [_vp, _vp]),
     "oibvh_mgpu_detach": (C.c_int, [_vp]),
@@ -667,6 +669,14 @@ class Scene:
 
     def detect_async(self, entryLevel=0, expandLevels=0):
         _check(_lib.oibvh_scene_detect_async(self._h, int(entryLevel), int(expandLevels)))
+
+    def set_self_collision(self, enable=True):
+        """also test every object against itself (non-adjacent triangle pairs of one mesh); opt-in extension"""
+        _check(_lib.oibvh_scene_set_self_collision(self._h, 1 if enable else 0))
+
+    def set_coherence(self, enable=True, cut_depth=0):
+        """temporal coherence: start detections from a recorded BVTT cut while the trees are only refitted; opt-in"""
+        _check(_lib.oibvh_scene_set_coherence(self._h, 1 if enable else 0, int(cut_depth)))
 
     def reserve(self, front_records=0, candidate_records=0, pair_records=0):
         """size the work queues up front (a multi-GPU scene cannot regrow them)"""

@@ -130,6 +130,7 @@ struct oibvh_tree
     bool consumed_recorded = false;
     bool upload_pending = false; // staging buffer holds positions that have not been packed yet
     uint64_t epoch = 0;          // bumped by everything that changes what a detection would read (positions, nodes)
+    uint64_t build_serial = 0;   // bumped by every build: a recorded BVTT cut is tied to the face order it was made on
 };
 
 struct oibvh_scene
@@ -164,6 +165,14 @@ struct oibvh_scene
     // the trees' modification counters when the last detection was enqueued (an overflow re-run is only valid if
     // nothing has touched them since)
     std::vector<uint64_t> enq_epochs;
+    // opt-in extensions
+    bool self_collision = false; // also test every object against itself
+    bool coherent = false;       // temporal coherence: detections start from a recorded BVTT cut while it is valid
+    uint32_t cut_depth = 6;      // the cut lies this many levels above the leaves
+    uint4* cut = nullptr;        // cand_cap records
+    bool cut_valid = false;
+    uint32_t last_mode = 0;      // mode of the last enqueued detection (0 plain, 1 recording, 2 from the cut)
+    std::vector<uint64_t> cut_sig; // what the cut was recorded on: scene set-up + the build serial of every tree
 };
 
 namespace
@@ -327,6 +336,9 @@ void scene_free_buffers(oibvh_scene* s)
 {
     cudaFree(s->queue);
     cudaFree(s->pair_block);
+    cudaFree(s->cut);
+    s->cut = nullptr;
+    s->cut_valid = false;
     s->queue = s->pairs = s->pair_block = nullptr;
     s->counters = s->counters_own;
 }
@@ -338,8 +350,10 @@ int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, u
     int rc;
     static_assert(CTR_WORDS * sizeof(uint32_t) % sizeof(uint4) == 0, "the counter block is a whole number of records");
     constexpr size_t kCtrRecords = CTR_WORDS * sizeof(uint32_t) / sizeof(uint4);
-    // (cand_cap is kept for the interface: candidates are tested by the warp that finds them and never stored)
-    if ((rc = dev_alloc(&s->queue, front_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)))
+    // (candidates are tested by the warp that finds them and never stored: cand_cap sizes the BVTT cut of a scene
+    // with temporal coherence instead)
+    if ((rc = dev_alloc(&s->queue, front_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)) ||
+        (s->coherent && (rc = dev_alloc(&s->cut, cand_cap))))
         return rc;
     {
         cudaError_t e = cudaMemsetAsync(s->queue, 0xff, sizeof(uint4) * (size_t)front_cap, s->ctx->stream);
@@ -751,6 +765,7 @@ static int tree_copy_state(oibvh_tree* dst, const oibvh_tree* src, bool with_fac
     dst->built = src->built;
     dst->upload_pending = false;
     dst->epoch++;
+    dst->build_serial++;
     return OIBVH_OK;
 }
 
@@ -890,6 +905,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
         count_launch(ctx);
         tree->built = true;
         tree->epoch++;
+        tree->build_serial++;
         return OIBVH_OK;
     }
     const size_t radix = (size_t)1 << kRadixBits;
@@ -939,6 +955,7 @@ extern "C" int oibvh_tree_build(oibvh_tree* tree)
     count_launch(ctx);
     tree->built = true;
     tree->epoch++;
+    tree->build_serial++;
     return OIBVH_OK;
 }
 
@@ -1022,6 +1039,7 @@ extern "C" int oibvh_tree_build_many(oibvh_tree* const* trees, uint32_t n)
         {
             t->built = true;
             t->epoch++;
+            t->build_serial++;
         }
     }
     if (large_list.empty()) return OIBVH_OK;
@@ -1109,6 +1127,7 @@ static int build_large_many(oibvh_tree* const* trees, uint32_t n)
         count_launch(ctx);
         t->built = true;
         t->epoch++;
+        t->build_serial++;
     }
     CU(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -1444,6 +1463,15 @@ extern "C" int oibvh_scene_create(oibvh_ctx* ctx, oibvh_scene** out)
         return fail(OIBVH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
     }
     memset(s->h_counters, 0, sizeof(uint32_t) * CTR_WORDS);
+    rc = dev_alloc(&s->mg_state, (size_t)MG_WORDS); // persistent words: multi-GPU protocol, size of the recorded cut
+    if (rc == OIBVH_OK && cudaMemset(s->mg_state, 0, sizeof(uint32_t) * MG_WORDS) != cudaSuccess) rc = OIBVH_ERR_CUDA;
+    if (rc)
+    {
+        cudaFree(s->counters_own);
+        cudaFreeHost(s->h_counters);
+        delete s;
+        return rc;
+    }
     *out = s;
     return OIBVH_OK;
 }
@@ -1564,6 +1592,33 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     }
     const uint32_t rounds = CTR_MAX_ROUNDS - 1; // statistics: one counter per tree level
 
+    // temporal coherence: record the cut on the first detection (and whenever what it was recorded on has changed),
+    // start from it otherwise. Scenes beyond the few-pairs regime (a cut would hold O(n^2) disjoint root pairs) always
+    // start from the roots.
+    DetectOpts opt{};
+    opt.self = s->self_collision ? 1u : 0u;
+    opt.cut = s->cut;
+    opt.cut_cap = s->cand_cap;
+    opt.cut_depth = s->cut_depth;
+    opt.cut_state = s->mg_state + MG_CUT;
+    const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2 + (s->self_collision ? n_obj : 0);
+    if (rerun)
+        opt.mode = s->last_mode == 2 ? 2u : (s->last_mode == 1 ? 1u : 0u);
+    else if (s->coherent && s->cut && n_pairs <= 4096)
+    {
+        std::vector<uint64_t> sig = {n_obj, s->rank, s->world, k0, expand_levels, opt.self, s->cut_depth, s->cand_cap};
+        for (auto* t : s->trees) sig.push_back(t->build_serial);
+        if (s->cut_valid && sig == s->cut_sig)
+            opt.mode = 2;
+        else
+        {
+            REQUIRE(!ctx->capturing, "the first detection of a coherent scene records the cut: run it before capturing");
+            opt.mode = 1;
+            s->cut_sig = sig;
+            s->cut_valid = true;
+        }
+    }
+    s->last_mode = opt.mode;
     MgpuArgs mg{};
     mg.mode = (uint32_t)s->mg_mode;
     mg.world = s->world;
@@ -1589,7 +1644,7 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
         // broad and narrow phase run inside one persistent kernel; the stage clock covers both
         StageScope scope(ctx, OIBVH_STAGE_BROAD);
         CU(launch_collide(ctx->collide_grid, s->d_objs, n_obj, s->queue, s->front_cap, s->pairs, s->pair_cap,
-                          s->counters, k0, expand_levels, s->rank, s->world, mg, st));
+                          s->counters, k0, expand_levels, s->rank, s->world, mg, opt, st));
         count_launch(ctx);
     }
     s->enq_epochs.resize(s->trees.size());
@@ -1598,6 +1653,34 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     s->last_entry = entry_level;
     s->last_expand = requested_expand;
     s->last_rounds = rounds;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_set_self_collision(oibvh_scene* scene, int enable)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    scene->self_collision = enable != 0;
+    scene->cut_valid = false;
+    return OIBVH_OK;
+}
+
+extern "C" int oibvh_scene_set_coherence(oibvh_scene* scene, int enable, uint32_t cut_depth)
+{
+    REQUIRE(scene != nullptr, "scene is NULL");
+    oibvh_ctx* ctx = scene->ctx;
+    REQUIRE(!ctx->capturing, "set_coherence outside a graph capture");
+    REQUIRE(scene->mg_mode == 0 || !enable || scene->cut != nullptr, "enable coherence before oibvh_mgpu_export / attach");
+    DeviceGuard g(ctx->device);
+    scene->coherent = enable != 0;
+    scene->cut_depth = cut_depth ? std::min(cut_depth, 24u) : 6u;
+    scene->cut_valid = false;
+    if (scene->coherent && !scene->cut && scene->front_cap > 0)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        int rc = dev_alloc(&scene->cut, (size_t)scene->cand_cap);
+        if (rc) return rc;
+        ctx->generation++;
+    }
     return OIBVH_OK;
 }
 
@@ -1635,11 +1718,7 @@ static_assert(sizeof(MgpuHandleLayout) <= sizeof(oibvh_mgpu_handle), "handle lay
 
 int mgpu_state_alloc(oibvh_scene* s)
 {
-    if (!s->mg_state)
-    {
-        int rc = dev_alloc(&s->mg_state, (size_t)MG_WORDS);
-        if (rc) return rc;
-    }
+    s->cut_valid = false; // (the words of the protocol and of the cut share the block)
     CU(cudaMemsetAsync(s->mg_state, 0, sizeof(uint32_t) * MG_WORDS, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream));
     return OIBVH_OK;
@@ -1773,7 +1852,7 @@ extern "C" int oibvh_scene_detect_async(oibvh_scene* scene, uint32_t entry_level
             if (rc) return rc;
         }
     }
-    if (scene->trees.size() < 2)
+    if (scene->trees.size() < 2 && !scene->self_collision)
     {
         // a single object has no pairs i<j (the reference loops over i<j only, scene.cu:195-196)
         CU(cudaMemsetAsync(scene->counters, 0, sizeof(uint32_t) * CTR_WORDS, ctx->stream));
@@ -1818,7 +1897,9 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         }
         // a queue overflowed: grow (counts keep counting past the capacity, so they are lower bounds) and redo
         uint32_t fc = scene->front_cap, cc = scene->cand_cap, pc = scene->pair_cap;
+        scene->cut_valid = false; // a detection that overflowed has not recorded a complete cut
         if (h[CTR_OVERFLOW] & 1u) fc = grow_to(fc, max_front); // every BVTT node of the traversal passes through the queue
+        if (h[CTR_OVERFLOW] & 2u) cc = grow_to(cc, h[CTR_CUT]);
         if (h[CTR_OVERFLOW] & 4u) pc = grow_to(pc, h[CTR_PAIRS]);
         if (fc == scene->front_cap && cc == scene->cand_cap && pc == scene->pair_cap)
             return fail(OIBVH_ERR_OVERFLOW, "work queues cannot grow further");

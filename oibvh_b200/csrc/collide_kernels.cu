@@ -83,9 +83,12 @@ __device__ __forceinline__ bool queue_retire(uint32_t* counters, uint32_t n)
 // Round 0 of the expansion turns them into the reference's entry-level seed rectangle (scene.cu:192-223)
 // and prunes object pairs whose root boxes do not overlap.
 // ---------------------------------------------------------------------------------------------------
-// p-th object pair (i < j), row-major over the strict upper triangle of the n_obj x n_obj matrix
+// p-th object pair (i < j), row-major over the strict upper triangle of the n_obj x n_obj matrix; with self-collision
+// the n pairs (i, i) follow the n (n - 1) / 2 pairs of distinct objects
 __device__ __forceinline__ uint4 seed_entry(uint32_t n_obj, uint64_t p)
 {
+    const uint64_t distinct = (uint64_t)n_obj * (n_obj - 1) / 2;
+    if (p >= distinct) return make_uint4((uint32_t)(p - distinct), (uint32_t)(p - distinct), 0u, 0u);
     const double nd = (double)n_obj;
     uint32_t i = (uint32_t)floor((2.0 * nd - 1.0 - sqrt((2.0 * nd - 1.0) * (2.0 * nd - 1.0) - 8.0 * (double)p)) * 0.5);
     while ((uint64_t)i * (2ull * n_obj - i - 1) / 2 > p) i--; // fix the rounding of the closed form
@@ -184,6 +187,7 @@ __device__ void seed_phase(float* __restrict__ s_roots, const ObjDesc* __restric
 // linear index of the object pair (i, j), i < j: the inverse of seed_entry (deterministic shard key)
 __device__ __forceinline__ uint32_t pair_linear(uint32_t n_obj, uint32_t i, uint32_t j)
 {
+    if (i == j) return (uint32_t)((uint64_t)n_obj * (n_obj - 1) / 2) + i; // self-collision pair
     return (uint32_t)((uint64_t)i * (2ull * n_obj - i - 1) / 2) + (j - i - 1);
 }
 
@@ -337,7 +341,10 @@ struct EmitShared
     uint32_t queue_cap;
     uint32_t pair_cap;
     uint32_t remote;
-    uint32_t pad;
+    uint32_t record;     // 1 = this detection records the BVTT cut (temporal coherence, see record_cut)
+    uint4* cut;
+    uint32_t cut_cap;
+    uint32_t cut_depth;  // levels above the leaves at which the cut lies
     ObjDesc s_objs[kObjCache];
 };
 struct Emit
@@ -373,9 +380,15 @@ __device__ OIBVH_SAT_INLINE void narrow_staged(const EmitShared& sh, const uint4
             const ObjDesc A = get_obj(sh.s_objs, sh.objs, c.x), B = get_obj(sh.s_objs, sh.objs, c.y);
             const uint32_t* fa = A.faces + 3ull * c.z;
             const uint32_t* fb = B.faces + 3ull * c.w;
-            const V3 P1 = load_v3(A.pos, __ldg(fa)), P2 = load_v3(A.pos, __ldg(fa + 1)), P3 = load_v3(A.pos, __ldg(fa + 2));
-            const V3 Q1 = load_v3(B.pos, __ldg(fb)), Q2 = load_v3(B.pos, __ldg(fb + 1)), Q3 = load_v3(B.pos, __ldg(fb + 2));
-            hit = triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
+            const uint32_t a0 = __ldg(fa), a1 = __ldg(fa + 1), a2 = __ldg(fa + 2);
+            const uint32_t b0 = __ldg(fb), b1 = __ldg(fb + 1), b2 = __ldg(fb + 2);
+            // self-collision: two triangles of ONE mesh that share a vertex always touch there -- they are neighbours,
+            // not a collision (decided before the test so that the six indices are dead during it)
+            const bool neighbours = c.x == c.y && (a0 == b0 || a0 == b1 || a0 == b2 || a1 == b0 || a1 == b1 || a1 == b2 ||
+                                                   a2 == b0 || a2 == b1 || a2 == b2);
+            const V3 P1 = load_v3(A.pos, a0), P2 = load_v3(A.pos, a1), P3 = load_v3(A.pos, a2);
+            const V3 Q1 = load_v3(B.pos, b0), Q2 = load_v3(B.pos, b1), Q3 = load_v3(B.pos, b2);
+            hit = !neighbours && triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, hit);
         if (mask)
@@ -441,6 +454,31 @@ __device__ __forceinline__ void flush_queue(Emit& e, uint32_t lane)
     e.staged_f = 0;
 }
 
+// Temporal coherence (the reference restarts from entryLevel every frame, src/cuda/scene.cu:236). A
+// recording detection writes down a complete CUT of the BVTT: every tested node pair that did NOT overlap above the
+// cut depth (its whole subtree was pruned) and every tested pair, overlapping or not, at the cut depth. While the trees
+// are only refitted the topology is fixed, so the next detections need not walk down from the roots: they re-test the
+// pairs of the cut (cut_seed_phase) and descend below those that overlap now -- exact for any motion, cheapest when
+// little has changed. `tested`/`hit` per lane, records with (level << 26 | position) on both sides.
+__device__ __forceinline__ void record_cut(const EmitShared& sh, uint32_t lane, bool misses, bool hits, bool t0, bool t1,
+                                           bool hit0, bool hit1, const uint4& r0, const uint4& r1)
+{
+    const bool w0 = t0 && ((hit0 && hits) || (!hit0 && misses)), w1 = t1 && ((hit1 && hits) || (!hit1 && misses));
+    const uint32_t m0 = __ballot_sync(0xffffffffu, w0), m1 = __ballot_sync(0xffffffffu, w1);
+    const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
+    if (n == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(sh.counters + CTR_CUT, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > sh.cut_cap)
+    {
+        if (lane == 0) atomicOr(sh.counters + CTR_OVERFLOW, 2u);
+        return;
+    }
+    if (w0) sh.cut[base + __popc(m0 & lanemask_lt())] = r0;
+    if (w1) sh.cut[base + n0 + __popc(m1 & lanemask_lt())] = r1;
+}
+
 // stage up to 64 overlapping descendant pairs of one item (two per lane) as queue records or candidates
 __device__ __forceinline__ void stage_hits(Emit& e, uint32_t lane, bool to_cand, bool hit0, bool hit1, const uint4& r0,
                                            const uint4& r1)
@@ -486,6 +524,7 @@ __device__ __forceinline__ LevelView level_view(const uint32_t* s_lv, uint32_t o
 // Seeding of scenes with few object pairs
 // ---------------------------------------------------------------------------------------------------
 // Root pairs: global warp w tests the root boxes of object pairs w, w + W, ... and queues the overlapping ones.
+template <bool RECORD>
 __device__ void root_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs, uint32_t n_obj)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -493,7 +532,7 @@ __device__ void root_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs,
     for (uint32_t p0 = (blockIdx.x * kColWarps + warp) * 32; p0 < n_pairs; p0 += total)
     {
         const uint32_t p = p0 + lane;
-        bool hit = false;
+        bool hit = false, shallow = false;
         uint4 it = make_uint4(0, 0, 0, 0);
         if (p < n_pairs)
         {
@@ -501,7 +540,11 @@ __device__ void root_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs,
             const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
             hit = box_overlap(load_box(reinterpret_cast<const float2*>(A.nodes), 0),
                               load_box(reinterpret_cast<const float2*>(B.nodes), 0));
+            shallow = max(A.L, B.L) <= e.sh.cut_depth;
         }
+        // the cut: a disjoint root pair prunes its whole BVTT; an overlapping one belongs to the cut if the trees are
+        // no deeper than the cut depth
+        if (RECORD) record_cut(e.sh, lane, true, shallow, p < n_pairs, false, hit, false, it, it);
         stage_hits(e, lane, false, hit, false, it, it);
     }
     flush_queue(e, lane);
@@ -512,6 +555,7 @@ __device__ void root_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs,
 // directly, spread over every warp of the grid: 4^8 = 65 K .. 4^11 = 4 M box tests are less work than the hops they
 // replace. A level is a contiguous slice, so a warp's 32 consecutive combinations read one broadcast box of A and 32
 // consecutive boxes of B. `rank`/`world` deal the combinations to the shards.
+template <bool RECORD, bool SELF>
 __device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs, uint32_t k0, uint32_t rank,
                                  uint32_t world, uint32_t n_obj)
 {
@@ -525,7 +569,13 @@ __device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs
         const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
         const float2* nodesA = reinterpret_cast<const float2*>(A.nodes);
         const float2* nodesB = reinterpret_cast<const float2*>(B.nodes);
-        if (!box_overlap(load_box(nodesA, 0), load_box(nodesB, 0))) continue; // disjoint roots (warp-uniform)
+        if (!box_overlap(load_box(nodesA, 0), load_box(nodesB, 0)))
+        {
+            // disjoint roots (warp-uniform): one cut record prunes the whole pair
+            if (RECORD && gw == 0) record_cut(e.sh, lane, true, false, lane == 0, false, false, false, it, it);
+            continue;
+        }
+        const bool self = SELF && it.x == it.y;
         const uint32_t ka = min(k0, A.L), kb = min(k0, B.L);
         const uint32_t nA = va.count(ka), nB = vb.count(kb), baseA = va.offset(ka), baseB = vb.offset(kb);
         const bool to_cand = (ka == A.L) && (kb == B.L);
@@ -534,7 +584,7 @@ __device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs
         for (uint32_t c0 = gw * 64; c0 < total; c0 += total_warps * 64)
         {
             const uint32_t c[2] = {c0 + lane, c0 + 32 + lane};
-            bool hit[2];
+            bool hit[2], tested[2];
             uint32_t ia[2], ib[2];
             Box a[2], b[2];
 #pragma unroll
@@ -543,6 +593,9 @@ __device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs
                 hit[u] = c[u] < total && (world == 1 || ((p + c[u]) % world) == rank);
                 ia[u] = c[u] / nB;
                 ib[u] = c[u] - ia[u] * nB;
+                // self-collision: the BVTT of a tree with itself is symmetric -- keep a <= b (a < b between leaves)
+                if (self) hit[u] = hit[u] && (to_cand ? ia[u] < ib[u] : ia[u] <= ib[u]);
+                tested[u] = hit[u];
                 if (hit[u])
                 {
                     a[u] = load_box(nodesA, baseA + ia[u]);
@@ -552,9 +605,42 @@ __device__ void dense_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_pairs
 #pragma unroll
             for (int u = 0; u < 2; u++)
                 if (hit[u]) hit[u] = box_overlap(a[u], b[u]);
+            if (RECORD) // misses always (pruned subtrees), hits if this level is already at / below the cut depth
+                record_cut(e.sh, lane, true, max(A.L - ka, B.L - kb) <= e.sh.cut_depth, tested[0], tested[1], hit[0], hit[1],
+                           make_uint4(it.x, it.y, (ka << kNodeLevelShift) + ia[0], (kb << kNodeLevelShift) + ib[0]),
+                           make_uint4(it.x, it.y, (ka << kNodeLevelShift) + ia[1], (kb << kNodeLevelShift) + ib[1]));
             stage_hits(e, lane, to_cand, hit[0], hit[1], make_uint4(it.x, it.y, za + ia[0], zb + ib[0]),
                        make_uint4(it.x, it.y, za + ia[1], zb + ib[1]));
         }
+    }
+    flush_queue(e, lane);
+    flush_candidates(e, lane);
+}
+
+// Replay of a recorded cut (temporal coherence): every warp of the grid takes 32 records at a time; a record whose two
+// boxes overlap NOW is queued (or, between two leaves, staged as a candidate) and the traversal descends below it.
+__device__ void cut_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_cut)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t stride = gridDim.x * kColWarps * 32;
+    for (uint32_t i0 = (blockIdx.x * kColWarps + warp) * 32; i0 < n_cut; i0 += stride)
+    {
+        const uint32_t i = i0 + lane;
+        bool hit = false, leaf = false;
+        uint4 it = make_uint4(0, 0, 0, 0);
+        if (i < n_cut)
+        {
+            it = e.sh.cut[i];
+            const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
+            const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
+            const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
+            const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
+            hit = box_overlap(load_box(reinterpret_cast<const float2*>(A.nodes), va.offset(la) + pa),
+                              load_box(reinterpret_cast<const float2*>(B.nodes), vb.offset(lb) + pb));
+            leaf = la == A.L && lb == B.L;
+        }
+        stage_hits(e, lane, false, hit && !leaf, false, it, it);
+        stage_hits(e, lane, true, hit && leaf, false, make_uint4(it.x, it.y, it.z & kNodePosMask, it.w & kNodePosMask), it);
     }
     flush_queue(e, lane);
     flush_candidates(e, lane);
@@ -604,6 +690,7 @@ extern "C" int oibvh_debug_collide_profile(unsigned long long* out, int reset)
 #define COL_ADD(slot, val)
 #endif
 
+template <bool RECORD, bool SELF>
 __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, volatile uint32_t* s_ctl,
                                uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, uint32_t n_obj,
                                uint32_t seeded)
@@ -725,7 +812,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         COL_ADD(6, t1b - t1);
 
         // ---- phase 1: lane l prepares its item ----
-        uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, key = 0;
+        uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, meta2 = 0, key = 0;
         uint64_t ptrA = 0, ptrB = 0;
         bool work = false;
         if (valid)
@@ -735,7 +822,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
             const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
             const uint32_t lb = it.w >> kNodeLevelShift, pb = it.w & kNodePosMask;
             const bool root = (it.z | it.w) == 0u;
-            const uint32_t k = root ? levels0 : levels;
+            // (a root pair reaches the queue when the seeding is not dense, or when a replayed cut holds one)
+            const uint32_t k = root ? min(levels0, kMaxExpandLevels) : levels;
             const uint32_t da = min(k, A.L - la), db = min(k, B.L - lb);
             const uint32_t lca = la + da, lcb = lb + db;
             const uint32_t fa = pa << da, fb = pb << db;
@@ -766,6 +854,14 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                    ((root && world > 1) ? 1u << 22 : 0u);
             // the children of a root pair are dealt round-robin to the shards, keyed by the pair's linear index
             key = pair_linear(n_obj, it.x, it.y);
+            // recording: levels of the children, and whether their misses / hits belong to the cut (depth above the
+            // leaves before and after this hop)
+            if (RECORD)
+            {
+                const uint32_t parent_rem = max(A.L - la, B.L - lb), rem = max(A.L - lca, B.L - lcb);
+                meta2 = lca | (lcb << 5) | ((parent_rem > e.sh.cut_depth) ? 1u << 10 : 0u) |
+                        ((rem <= e.sh.cut_depth && e.sh.cut_depth < parent_rem) ? 1u << 11 : 0u);
+            }
             atomicAdd(s_hist + min(la, 31u), 1u); // items per tree level of side A (oibvh_scene_get_round_stats)
         }
         COL_T(t1c);
@@ -783,6 +879,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
             const uint32_t exk = __shfl_sync(0xffffffffu, ex, k), eyk = __shfl_sync(0xffffffffu, ey, k);
             const uint32_t zak = __shfl_sync(0xffffffffu, za, k), zbk = __shfl_sync(0xffffffffu, zb, k);
             const uint32_t kk = __shfl_sync(0xffffffffu, key, k);
+            const bool self = SELF && exk == eyk;
             for (uint32_t g0 = 0; g0 < combos; g0 += 64) // warp-uniform
             {
                 const uint32_t c0 = g0 + lane, c1 = c0 + 32;
@@ -808,6 +905,14 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     ia1 = c1 / nB;
                     ib1 = c1 - ia1 * nB;
                 }
+                if (self)
+                {
+                    // self-collision: the BVTT of a tree with itself is symmetric -- keep a <= b (a < b between leaves);
+                    // both sides are at the same level, so the node ids compare like the positions
+                    hit0 = hit0 && (to_cand ? zak + ia0 < zbk + ib0 : zak + ia0 <= zbk + ib0);
+                    hit1 = hit1 && (to_cand ? zak + ia1 < zbk + ib1 : zak + ia1 <= zbk + ib1);
+                }
+                const bool t0 = hit0, t1 = hit1;
                 Box a0, b0, a1, b1;
                 if (hit0)
                 {
@@ -821,6 +926,15 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                 }
                 if (hit0) hit0 = box_overlap(a0, b0);
                 if (hit1) hit1 = box_overlap(a1, b1);
+                if (RECORD)
+                {
+                    const uint32_t m2 = __shfl_sync(0xffffffffu, meta2, k);
+                    const uint32_t la_c = (m2 & 31u) << kNodeLevelShift, lb_c = ((m2 >> 5) & 31u) << kNodeLevelShift;
+                    const uint32_t pa0 = (zak & kNodePosMask) + ia0, pb0 = (zbk & kNodePosMask) + ib0;
+                    const uint32_t pa1 = (zak & kNodePosMask) + ia1, pb1 = (zbk & kNodePosMask) + ib1;
+                    record_cut(e.sh, lane, (m2 >> 10) & 1u, (m2 >> 11) & 1u, t0, t1, hit0, hit1,
+                               make_uint4(exk, eyk, la_c | pa0, lb_c | pb0), make_uint4(exk, eyk, la_c | pa1, lb_c | pb1));
+                }
                 stage_hits(e, lane, to_cand, hit0, hit1, make_uint4(exk, eyk, zak + ia0, zbk + ib0),
                            make_uint4(exk, eyk, zak + ia1, zbk + ib1));
             }
@@ -852,11 +966,16 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 // ---------------------------------------------------------------------------------------------------
 constexpr size_t kColStageBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 128 KB
 constexpr size_t kColSmemBytes = kColStageBytes;
+// MODE: 0 = from the roots, 1 = from the roots + write the BVTT cut down, 2 = from the recorded cut (temporal
+// coherence); SELF = objects are also tested against themselves: separate instantiations, so that the options do not cost the everyday kernel registers (it runs at
+// the 128-register cap without spilling; with the options compiled in it spilled and lost 10 %)
+template <int MODE, bool SELF>
 __global__ void __launch_bounds__(kColThreads, 1)
     collide_kernel(const ObjDesc* __restrict__ objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap, uint4* pairs,
                    uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world,
-                   const MgpuArgs mg)
+                   const MgpuArgs mg, const DetectOpts opt)
 {
+    constexpr bool RECORD = MODE == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_stage = reinterpret_cast<uint4*>(smem_raw); // kColWarps x kStageCap records
     __shared__ __align__(16) EmitShared s_emit;
@@ -885,6 +1004,10 @@ __global__ void __launch_bounds__(kColThreads, 1)
         s_emit.pairs = remote ? mg.root_pairs : pairs;
         s_emit.pair_cap = remote ? mg.root_pair_cap : pair_cap;
         s_emit.pair_ctr = remote ? mg.root_counters : counters;
+        s_emit.record = RECORD ? 1u : 0u;
+        s_emit.cut = opt.cut;
+        s_emit.cut_cap = opt.cut_cap;
+        s_emit.cut_depth = opt.cut_depth;
     }
     // multi-GPU: this launch is frame MG_FRAME + 1 of the scene. A remote rank may append to the root's list only once
     // the root has zeroed its counter block for this frame (MG_OPEN >= frame): one thread per CTA polls the root's word
@@ -934,17 +1057,31 @@ __global__ void __launch_bounds__(kColThreads, 1)
     // ---- seeds: queue records for the object pairs whose root boxes overlap ----
     // few pairs (the common two-body scene): every node pair of a deep level tested densely, or the root pairs
     // themselves; many-body scenes: the tiled top-level pass over the root boxes
-    const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2;
+    const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2 + (SELF ? n_obj : 0u);
     const bool dense = n_pairs <= 4096 && levels0 > kMaxExpandLevels;
-    if (dense)
-        dense_seed_phase(e, s_lv, (uint32_t)n_pairs, levels0, rank, world, n_obj);
+    if (MODE == 2)
+        cut_seed_phase(e, s_lv, __ldcg(opt.cut_state)); // temporal coherence: start from the recorded cut
+    else if (dense)
+        dense_seed_phase<RECORD, SELF>(e, s_lv, (uint32_t)n_pairs, levels0, rank, world, n_obj);
     else if (n_pairs <= 4096)
-        root_seed_phase(e, s_lv, (uint32_t)n_pairs, n_obj);
+        root_seed_phase<RECORD>(e, s_lv, (uint32_t)n_pairs, n_obj);
     else
+    {
         seed_phase(reinterpret_cast<float*>(smem_raw), objs, n_obj, queue, queue_cap, counters);
+        if (SELF)
+        {
+            // self-collision: every object against itself
+            __syncthreads(); // the tile staging area is the warps' staging area again
+            const uint32_t lane = lane_id();
+            for (uint32_t i0 = (blockIdx.x * kColWarps + warp) * 32; i0 < n_obj; i0 += gridDim.x * kColWarps * 32)
+                stage_hits(e, lane, false, i0 + lane < n_obj, false, make_uint4(i0 + lane, i0 + lane, 0u, 0u),
+                           make_uint4(0, 0, 0, 0));
+            flush_queue(e, lane);
+        }
+    }
     const uint32_t seeded = grid_barrier(counters, 1, counters + CTR_Q_TAIL);
     stamp();
-    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded);
+    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded);
     __syncthreads();
     stamp();
 
@@ -956,6 +1093,9 @@ __global__ void __launch_bounds__(kColThreads, 1)
             queue[i] = make_uint4(kQEmpty, kQEmpty, kQEmpty, kQEmpty);
     }
     if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(counters + CTR_FRONT0 + threadIdx.x, s_hist[threadIdx.x]);
+    // a recording detection leaves the size of the cut where the replaying ones find it (every record was written
+    // before the traversal stopped; the slowest CTA may write the word last, they all write the same value)
+    if (RECORD && threadIdx.x == 0) st_relaxed_gpu(opt.cut_state, min(__ldcg(counters + CTR_CUT), opt.cut_cap));
     stamp();
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_TIME0 - 1] = n_stamps; // number of stamps
     if (mg.mode != 0 && threadIdx.x == 0)
@@ -1096,14 +1236,27 @@ cudaError_t launch_box_wireframe(const float* nodes, uint32_t n, float* verts, u
     return cudaGetLastError();
 }
 
+static const void* collide_fn(uint32_t mode, bool self)
+{
+    if (mode == 1) return self ? (const void*)collide_kernel<1, true> : (const void*)collide_kernel<1, false>;
+    if (mode == 2) return self ? (const void*)collide_kernel<2, true> : (const void*)collide_kernel<2, false>;
+    return self ? (const void*)collide_kernel<0, true> : (const void*)collide_kernel<0, false>;
+}
+
 cudaError_t collide_configure(int* grid_blocks)
 {
-    cudaError_t e = cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0, sms = 0, dev = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collide_kernel, kColThreads, kColSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaGetDevice(&dev);
+    int per_sm = 1 << 20, sms = 0, dev = 0;
+    for (int v = 0; v < 6; v++)
+    {
+        const void* fn = collide_fn(v >> 1, v & 1);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kColThreads, kColSmemBytes);
+        if (e != cudaSuccess) return e;
+        per_sm = n < per_sm ? n : per_sm;
+    }
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
@@ -1114,12 +1267,13 @@ cudaError_t collide_configure(int* grid_blocks)
 
 cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap,
                            uint4* pairs, uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels,
-                           uint32_t rank, uint32_t world, const MgpuArgs& mg, cudaStream_t s)
+                           uint32_t rank, uint32_t world, const MgpuArgs& mg, const DetectOpts& opt, cudaStream_t s)
 {
     MgpuArgs mga = mg;
-    void* args[] = {&objs, &n_obj, &queue, &queue_cap, &pairs, &pair_cap, &counters, &levels0, &levels, &rank, &world, &mga};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(collide_kernel), dim3(grid_blocks),
-                                       dim3(kColThreads), args, kColSmemBytes, s);
+    DetectOpts o = opt;
+    void* args[] = {&objs, &n_obj, &queue, &queue_cap, &pairs, &pair_cap, &counters, &levels0, &levels, &rank, &world, &mga, &o};
+    return cudaLaunchCooperativeKernel(collide_fn(opt.mode, opt.self != 0), dim3(grid_blocks), dim3(kColThreads), args,
+                                       kColSmemBytes, s);
 }
 
 } // namespace oibvh

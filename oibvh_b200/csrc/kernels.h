@@ -105,8 +105,9 @@ enum
 {
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
-    CTR_OVERFLOW = 2, // bit 0: work queue, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out
+    CTR_OVERFLOW = 2, // bit 0: work queue, bit 1: cut buffer, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out
     CTR_BARRIER = 3,  // arrival counter of the grid barrier
+    CTR_CUT = 4,      // records written by a recording detection (temporal coherence)
     CTR_FRONT0 = 8,   // CTR_FRONT0 + l = BVTT nodes processed whose side-A node is at tree level l (statistics)
     CTR_MAX_ROUNDS = 32,
     CTR_TIME0 = 64,   // CTR_TIME0 + i = SM cycle counter (low 32 bits) of CTA 0 at phase boundary i
@@ -129,6 +130,7 @@ enum
     MG_DONE = 2,   // root only: remote completions so far (monotonic: every remote rank adds 1 per frame)
     MG_EXIT = 3,   // CTAs that have left the current launch (the last one re-arms it)
     MG_FAIL = 4,   // sticky: a wait timed out
+    MG_CUT = 8,    // temporal coherence: number of records of the recorded BVTT cut
     MG_WORDS = 64
 };
 struct MgpuArgs
@@ -141,6 +143,16 @@ struct MgpuArgs
     uint4* root_pairs;      // remote: the root's pair list
     uint32_t root_pair_cap;
 };
+// options of one detection
+struct DetectOpts
+{
+    uint32_t mode;       // 0 = from the roots, 1 = from the roots + record the BVTT cut, 2 = from the recorded cut
+    uint32_t self;       // also every object against itself (pairs of non-adjacent triangles of one mesh)
+    uint4* cut;          // cut records: (objA, objB, level << 26 | pos, level << 26 | pos)
+    uint32_t cut_cap;
+    uint32_t cut_depth;  // the cut lies this many levels above the leaves
+    uint32_t* cut_state; // persistent: [0] = number of records of the recorded cut
+};
 // root: zero the counter block of the coming frame, then publish MG_OPEN = frame (system scope)
 cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s);
 
@@ -152,7 +164,7 @@ cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s
 cudaError_t collide_configure(int* grid_blocks);
 cudaError_t launch_collide(int grid_blocks, const ObjDesc* objs, uint32_t n_obj, uint4* queue, uint32_t queue_cap,
                            uint4* pairs, uint32_t pair_cap, uint32_t* counters, uint32_t levels0, uint32_t levels,
-                           uint32_t rank, uint32_t world, const MgpuArgs& mg, cudaStream_t s);
+                           uint32_t rank, uint32_t world, const MgpuArgs& mg, const DetectOpts& opt, cudaStream_t s);
 
 // collided-triangle vertex stream (Scene::convertToVertexArray) and node-box wireframes
 // (OibvhTree::convertToVertexArray) as device-side gathers

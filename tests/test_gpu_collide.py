@@ -249,3 +249,149 @@ def test_pair_vertex_stream_and_wireframes(ctx, port, golden):
     assert_bit_equal(gv, g["box_vertices"], "golden box corners")
     for t in (ta, tb):
         t.close()
+
+
+# ---- opt-in extensions: temporal coherence and self-collision ------------------------------------
+def test_temporal_coherence_equals_detection_from_the_roots(ctx, port):
+    """a coherent scene records a BVTT cut once and starts the following detections from it: over a 100-frame rotation
+    (refit only) the pair set of every frame equals that of a detection from the roots, and the oracle's on samples"""
+    pos, faces = meshgen.blob(96, 72, seed=21)
+    faces = meshgen.shuffle_faces(faces)
+    mA, mB = ob.Mesh(pos, faces), ob.Mesh(pos, faces)
+    tA = ob.OibvhTree(mA, ctx=ctx)
+    tA.build()
+    tB = ob.OibvhTree(tA, mB)
+    M0 = mB.transform_matrix_translate((0.8, 0.1, 0.05))
+    mB.transform(M0)
+    tB.transform(M0)
+    tB.refit(upload=False)
+    plain, coh = ob.Scene(ctx), ob.Scene(ctx)
+    for sc in (plain, coh):
+        sc.addOibvhTree(tA)
+        sc.addOibvhTree(tB)
+    coh.set_coherence(True)
+    oa = port.build(pos, faces, mA.m_aabb)
+    sizes = set()
+    for frame in range(100):
+        R = mB.transform_matrix_rotate((0.3, 1.0, 0.2), 1.0)
+        mB.transform(R)
+        tB.transform(R)
+        tB.refit(upload=False)
+        plain.detect_async(4, 0)
+        coh.detect_async(4, 0)
+        want = plain.canonical_pairs()
+        assert coh.counts() == plain.counts(), f"frame {frame}"
+        assert np.array_equal(coh.canonical_pairs(), want), f"frame {frame}"
+        sizes.add(len(want))
+        if frame % 33 == 0:
+            nodesB = port.refit(mB.m_positions, oa["faces"])
+            pp, _ = port.detect([(oa["nodes"], oa["faces"], pos), (nodesB, oa["faces"], mB.m_positions)])
+            assert np.array_equal(want, oracle.canonical_pairs(pp, [oa["perm"], oa["perm"]])), f"frame {frame}"
+    assert len(sizes) > 10  # the contact really changed over the rotation
+    # a large jump (the bodies far apart, then deeply interpenetrating) is still exact: the cut is complete
+    for shift in ((5.0, 0.0, 0.0), (-5.6, -0.1, 0.0)):
+        M = mB.transform_matrix_translate(shift)
+        mB.transform(M)
+        tB.transform(M)
+        tB.refit(upload=False)
+        plain.detect_async(4, 0)
+        coh.detect_async(4, 0)
+        assert np.array_equal(coh.canonical_pairs(), plain.canonical_pairs())
+    assert len(plain.canonical_pairs()) > 0
+    # a rebuild changes the face order: the next coherent detection records a new cut, and stays exact
+    tB.build()
+    plain.detect_async(4, 0)
+    coh.detect_async(4, 0)
+    coh.detect_async(4, 0)
+    assert np.array_equal(coh.canonical_pairs(), plain.canonical_pairs())
+    # replayed from a graph
+    ctx.capture_begin()
+    tB.transform(mB.transform_matrix_rotate((0, 0, 1), 0.5))
+    tB.refit(upload=False)
+    coh.detect_async(4, 0)
+    g = ctx.capture_end()
+    for _ in range(3):
+        g.launch()
+    n_graph = coh.counts()
+    plain.detect_async(4, 0)
+    assert plain.counts() == n_graph and np.array_equal(coh.canonical_pairs(), plain.canonical_pairs())
+    g.close()
+
+
+@pytest.mark.parametrize("cut_depth", [3, 6, 9, 30])
+def test_temporal_coherence_cut_depths_and_three_bodies(ctx, port, golden, cut_depth):
+    """any cut depth (also deeper than the trees: the cut is then the root pairs) and more than two objects"""
+    g = golden["collide"]
+    meshes = [(g[f"body{k}_pos"], g[f"body{k}_faces"]) for k in range(3)]
+    sc, trees = make_scene(ctx, meshes)
+    sc.set_coherence(True, cut_depth)
+    for _ in range(3):
+        sc.detect_async(4, 3)
+        assert np.array_equal(sc.canonical_pairs(), g["bodies_pairs"])
+    M = ob.mat_translate(ob.mat_identity(), (0.05, -0.02, 0.03))
+    trees[1].transform(M)
+    trees[1].refit(upload=False)
+    sc.detect_async(4, 3)
+    got = sc.canonical_pairs()
+    sc2 = ob.Scene(ctx)
+    for t in trees:
+        sc2.addOibvhTree(t)
+    sc2.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    assert np.array_equal(got, sc2.canonical_pairs())
+
+
+def _self_collision_oracle(port, pos, faces):
+    """brute force: all pairs a < b of one mesh with overlapping boxes and no common vertex, through the oracle's SAT"""
+    boxes = port.leaf_aabbs(pos, faces)
+    out = []
+    lo, hi = boxes[:, :3], boxes[:, 3:]
+    for a in range(len(faces) - 1):
+        ov = np.all((lo[a] <= hi[a + 1:]) & (hi[a] >= lo[a + 1:]), axis=1)
+        for b in np.nonzero(ov)[0] + a + 1:
+            if len(set(faces[a]) & set(faces[b])):
+                continue
+            if port.tri_tri(pos[faces[a]], pos[faces[b]]):
+                out.append((0, 0, a, b))
+    return np.array(out, np.uint32).reshape(-1, 4)
+
+
+def test_self_collision_matches_brute_force(ctx, port):
+    """opt-in: a mesh against itself -- a folded sheet whose two halves pass through each other"""
+    pos, faces = meshgen.terrain(24, 20, height=0.0, size=(2.0, 2.0))
+    p = pos.astype(np.float64)
+    fold = p[:, 0] > 0.1
+    p[fold, 1] = 0.35 - 0.9 * (p[fold, 0] - 0.1)   # the right part is bent up and back down through the left part
+    p[fold, 0] = 0.1 - 0.8 * (p[fold, 0] - 0.1)
+    pos = p.astype(np.float32)
+    faces = meshgen.shuffle_faces(faces, seed=3)
+    want = _self_collision_oracle(port, pos, faces)
+    assert len(want) > 10
+    t = ob.OibvhTree(ob.Mesh(pos, faces), ctx=ctx)
+    t.build()
+    sc = ob.Scene(ctx)
+    sc.addOibvhTree(t)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    assert sc.getIntTriPairCount() == 0  # without the option a single object has no pairs (scene.cu:195-196)
+    sc.set_self_collision(True)
+    for entry, expand in ((4, 3), (0, 0), (2, 2)):
+        sc.detectCollision(ob.DeviceType.GPU0, entry, expand)
+        raw = sc.m_intTriPairs
+        assert (raw[:, 0] == 0).all() and (raw[:, 1] == 0).all() and (raw[:, 2] < raw[:, 3]).all()
+        perm = t.download()["perm"]
+        got = np.stack([raw[:, 0], raw[:, 1], perm[raw[:, 2]], perm[raw[:, 3]]], 1)
+        got[:, 2:] = np.sort(got[:, 2:], axis=1)  # input face ids of a pair, smaller first
+        got = got[np.lexsort((got[:, 3], got[:, 2]))]
+        assert np.array_equal(got, want[np.lexsort((want[:, 3], want[:, 2]))]), (entry, expand)
+    # together with a second object and with temporal coherence
+    pos2, faces2 = meshgen.icosphere(3, radius=0.3, center=(0.0, 0.1, 0.0))
+    t2 = ob.OibvhTree(ob.Mesh(pos2, faces2), ctx=ctx)
+    t2.build()
+    sc.addOibvhTree(t2)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 3)
+    both = sc.m_intTriPairs
+    sc.set_coherence(True)
+    for _ in range(2):
+        sc.detect_async(4, 3)
+        again = sc.m_intTriPairs
+        assert np.array_equal(again[np.lexsort(again.T[::-1])], both[np.lexsort(both.T[::-1])])
+    assert (both[:, 0] == both[:, 1]).sum() == len(want) and (both[:, 0] != both[:, 1]).sum() > 0
