@@ -683,6 +683,31 @@ def terrain_scene(g):
     return s
 
 
+def coherence_record(g, s, n=20):
+    """f4 beside the from-the-roots traversal, on a refit-only config: the same trees in a second, coherent scene (it
+    records a BVTT cut once and starts every detection from it); detection-only times, CUDA events, same pair set"""
+    ob = g.ob
+    coh = ob.Scene(g.ctx)
+    for t in s.trees:
+        coh.addOibvhTree(t)
+    coh.reserve(candidate_records=1 << 22)
+    coh.set_coherence(True)
+    plain = ob.Scene(g.ctx)
+    for t in s.trees:
+        plain.addOibvhTree(t)
+    out = {}
+    for name, sc in (("from_roots", plain), ("from_recorded_cut", coh)):
+        for _ in range(3):
+            sc.detect_async(ENTRY_LEVEL, EXPAND_LEVELS)
+            sc.counts()
+        out[name + "_ms"] = g.timed(lambda: sc.detect_async(ENTRY_LEVEL, EXPAND_LEVELS), n)
+        out[name + "_pairs"] = int(sc.counts()[0])
+    out["pair_set_equal"] = bool(np.array_equal(plain.canonical_pairs(), coh.canonical_pairs()))
+    plain.close()
+    coh.close()
+    return out
+
+
 def cpu_refit_detect(s, moving, label):
     """CPU path beside a refit-only config, rank 0 at N = 1: the oracle port refits the moving trees from the positions
     the device holds NOW and detects on the same trees; also the parity check of this config at full size (node arrays
@@ -763,9 +788,24 @@ def run_gpu_arm(args):
         rot_frames.append(torch.from_numpy(mb.m_positions.copy()).pin_memory())
     pair_host = torch.empty((max(8 * m1["pairs"], 1 << 16), 4), dtype=torch.int32).pin_memory()
 
+    # N > 1: every rank needs both position arrays, but eight ranks pulling the same 12.6 MB from host memory at once
+    # contend for it (measured: e2e 0.53 -> 0.77 ms at N = 8). The inputs cross PCIe ONCE, on rank 0, and reach the other
+    # GPUs over NVLink (one NCCL broadcast of both arrays on the frame's stream).
+    if dist is not None:
+        dev_in = torch.empty((2, V, 3), dtype=torch.float32, device=f"cuda:{dev}")
+
     def e2e_upload(i):
-        tree_a.set_positions_from_host_ptr(host_a.data_ptr())
-        tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
+        if dist is None:
+            tree_a.set_positions_from_host_ptr(host_a.data_ptr())
+            tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
+            return
+        with torch.cuda.stream(g.stream):
+            if rank == 0:
+                dev_in[0].copy_(host_a, non_blocking=True)
+                dev_in[1].copy_(rot_frames[i % len(rot_frames)], non_blocking=True)
+            dist.broadcast(dev_in, src=0)
+        tree_a.set_positions_from_device(dev_in[0].data_ptr())
+        tree_b.set_positions_from_device(dev_in[1].data_ptr())
 
     def e2e_frame(i, upload=True, prefetch=None):
         # both uploads are enqueued first (they run on the library's copy stream); body A's build + refit overlap
@@ -964,6 +1004,8 @@ def run_gpu_arm(args):
         if rank == 0:
             Td, Vd = len(s.faces), len(s.pos)
             extra["roofline"] = {"refit": frac(bytes_refit(Td, Vd), m["stage_ms"]["refit"])}
+            if world == 1:
+                extra["temporal_coherence"] = coherence_record(g, s)
             if world == 1 and not args.no_cpu_baseline:
                 extra["cpu_baseline"], extra["parity"] = cpu_refit_detect(s, {0}, "refit(4 M) + detect")
         finish(s, m, extra)
@@ -998,6 +1040,8 @@ def run_gpu_arm(args):
             Tb, Vb = len(s.bfaces), len(s.bpos)
             extra["roofline"] = {"terrain_build_once": frac(bytes_build(Tt, Vt), s.terrain_build_ms),
                                  "refit_body": frac(bytes_refit(Tb, Vb), m["stage_ms"]["refit"])}
+            if world == 1:
+                extra["temporal_coherence"] = coherence_record(g, s)
             if world == 1 and not args.no_cpu_baseline:
                 extra["cpu_baseline"], extra["parity"] = cpu_refit_detect(s, {1}, "refit(1 M body) + detect vs 16.8 M terrain")
         finish(s, m, extra)

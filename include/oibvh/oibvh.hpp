@@ -515,6 +515,13 @@ public:
         oibvh_detail::check(oibvh_scene_get_pairs(scene, reinterpret_cast<oibvh_int_tri_pair*>(m_intTriPairs.data())));
         m_lastScene = scene;
     }
+    // Opt-in extensions (see include/oibvh_b200.h): also test every object against itself, and start
+    // detections from a recorded BVTT cut while the trees are only refitted. Both apply to the GPU0 scene.
+    void setSelfCollision(bool enable) { oibvh_detail::check(oibvh_scene_set_self_collision(m_handle, enable ? 1 : 0)); }
+    void setTemporalCoherence(bool enable, unsigned int cutDepth = 0)
+    {
+        oibvh_detail::check(oibvh_scene_set_coherence(m_handle, enable ? 1 : 0, cutDepth));
+    }
     unsigned int getIntTriPairCount() const { return m_intTriPairCount; }
     unsigned int getCandidateCount() const { return m_candidateCount; } // extension
     // Scene::convertToVertexArray (src/cuda/scene.cu:68-93) without the GL upload: m_vertices = six vec3 per pair

@@ -105,21 +105,24 @@ __device__ __forceinline__ uint4 seed_entry(uint32_t n_obj, uint64_t p)
 // rows, so a pair costs two broadcast 128-bit shared-memory reads and the test, and a root box is fetched n / B
 // times in total instead of once per pair.
 __device__ void seed_phase(float* __restrict__ s_roots, const ObjDesc* __restrict__ objs, uint32_t n_obj,
-                           uint4* __restrict__ front, uint32_t front_cap, uint32_t* __restrict__ counters)
+                           uint4* __restrict__ front, uint32_t front_cap, uint32_t* __restrict__ counters, uint32_t rank,
+                           uint32_t world)
 {
+    // multi-GPU: the TILES are dealt to the ranks (tile t belongs to rank t mod world), so the top-level pass itself
+    // shrinks with the number of GPUs and an object pair lives on exactly one rank from the root down
     // (`front` is the work queue: a slot is claimed from its tail counter and filled with one 128-bit store)
     uint32_t bshift = 8;
     auto tiles_of = [&](uint32_t sh) {
         const uint32_t nb = (n_obj + (1u << sh) - 1) >> sh;
         return nb * (nb + 1) / 2;
     };
-    while (bshift > 5 && tiles_of(bshift) < gridDim.x) bshift--;
+    while (bshift > 5 && tiles_of(bshift) < gridDim.x * world) bshift--;
     const uint32_t B = 1u << bshift, nb = (n_obj + B - 1) >> bshift, tiles = nb * (nb + 1) / 2;
     const uint32_t lane = lane_id();
     float4* sa = reinterpret_cast<float4*>(s_roots);          // [B][2] row-block roots: (lx ly lz hx) (hy hz - -)
     float4* sb = reinterpret_cast<float4*>(s_roots) + 2 * B;  // [B][2] column-block roots
     uint32_t bi = 0, row_first = 0; // tile t = row_first(bi) + (bj - bi), rows of nb - bi tiles
-    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x)
+    for (uint32_t t = blockIdx.x * world + rank; t < tiles; t += gridDim.x * world)
     {
         while (t >= row_first + (nb - bi))
         {
@@ -665,6 +668,12 @@ __device__ void cut_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_cut)
 // equal knows that nothing is in flight and nothing can be pushed any more: it raises the stop flag. The hop latency is ~4 dependent L2 round trips
 // (claim, record, boxes, push) instead of a grid barrier on top of them, and hops of different subtrees overlap.
 // ---------------------------------------------------------------------------------------------------
+// The CTA's copy of (stop flag, queue tail) is written by whichever warp is on duty and read by all the others with no
+// barrier in between -- single words, any interleaving is fine. Shared-memory atomics make that explicit (to the reader
+// and to racecheck); they are issued by one lane, a few times per thousand cycles.
+__device__ __forceinline__ uint32_t ctl_load(volatile uint32_t* p) { return atomicOr(const_cast<uint32_t*>(p), 0u); }
+__device__ __forceinline__ void ctl_store(volatile uint32_t* p, uint32_t v) { atomicExch(const_cast<uint32_t*>(p), v); }
+
 #ifdef OIBVH_PROFILE
 // where the traversal's warps spend their time (summed over all warps, lane 0's clock): [0] window, [1] polls that
 // found nothing, [2] set-up + box tests + staging, [3] queue pushes, [4] narrow phase, [5] total, [6] polls that found
@@ -693,7 +702,7 @@ extern "C" int oibvh_debug_collide_profile(unsigned long long* out, int reset)
 template <bool RECORD, bool SELF>
 __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, volatile uint32_t* s_ctl,
                                uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, uint32_t n_obj,
-                               uint32_t seeded)
+                               uint32_t seeded, bool shard_roots)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 #ifdef OIBVH_PROFILE
@@ -738,7 +747,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                         if (queue_retire(ctr, e.retire))
                         {
                             st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
-                            s_ctl[0] = 1u;
+                            ctl_store(s_ctl, 1u);
                         }
                         e.retire = 0;
                     }
@@ -748,10 +757,10 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     //     -- refreshes a copy in shared memory; everybody else reads that.
                     if ((((uint32_t)clock64() >> 11) % kColWarps) == warp)
                     {
-                        s_ctl[1] = ld_relaxed_gpu(ctr + CTR_Q_TAIL);
-                        if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) s_ctl[0] = 1u;
+                        ctl_store(s_ctl + 1, ld_relaxed_gpu(ctr + CTR_Q_TAIL));
+                        if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) ctl_store(s_ctl, 1u);
                     }
-                    if (s_ctl[0])
+                    if (ctl_load(s_ctl))
                     {
                         state = 1;
                         break;
@@ -760,7 +769,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     {
                         atomicOr(ctr + CTR_OVERFLOW, 8u); // nothing arrived for seconds: report instead of hanging
                         st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
-                        s_ctl[0] = 1u;
+                        ctl_store(s_ctl, 1u);
                         state = 1;
                         break;
                     }
@@ -774,15 +783,15 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     if (queue_retire(ctr, e.retire))
                     {
                         st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
-                        s_ctl[0] = 1u;
+                        ctl_store(s_ctl, 1u);
                     }
                     e.retire = 0;
                 }
                 uint32_t spins = 0;
-                while (!s_ctl[0] && ++spins < (1u << 22))
+                while (!ctl_load(s_ctl) && ++spins < (1u << 22))
                 {
                     if ((((uint32_t)clock64() >> 11) % kColWarps) == warp && ld_relaxed_gpu(ctr + CTR_Q_STOP))
-                        s_ctl[0] = 1u;
+                        ctl_store(s_ctl, 1u);
                     __nanosleep(500);
                 }
                 state = 1;
@@ -796,7 +805,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         // once there are several nodes per warp (records of different producers may become visible out of order:
         // whatever lies behind a gap waits for the next turn) ----
         uint32_t window = 1;
-        if (lane == 0) window = min(32u, max(1u, 2u * max(e.tail_seen, s_ctl[1]) / total_warps));
+        if (lane == 0) window = min(32u, max(1u, 2u * max(e.tail_seen, ctl_load(s_ctl + 1)) / total_warps));
         window = __shfl_sync(0xffffffffu, window, 0);
         const uint64_t slot64 = (uint64_t)gw + (uint64_t)(next + lane) * total_warps;
         uint4 it = make_uint4(kQEmpty, 0, 0, 0);
@@ -851,7 +860,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
             za = to_cand ? fa : ((lca << kNodeLevelShift) | fa);
             zb = to_cand ? fb : ((lcb << kNodeLevelShift) | fb);
             meta = combos | (nB << 11) | (db << 17) | ((nB == (1u << db)) ? 1u << 20 : 0u) | (to_cand ? 1u << 21 : 0u) |
-                   ((root && world > 1) ? 1u << 22 : 0u);
+                   ((root && shard_roots) ? 1u << 22 : 0u);
             // the children of a root pair are dealt round-robin to the shards, keyed by the pair's linear index
             key = pair_linear(n_obj, it.x, it.y);
             // recording: levels of the children, and whether their misses / hits belong to the cut (depth above the
@@ -1067,21 +1076,22 @@ __global__ void __launch_bounds__(kColThreads, 1)
         root_seed_phase<RECORD>(e, s_lv, (uint32_t)n_pairs, n_obj);
     else
     {
-        seed_phase(reinterpret_cast<float*>(smem_raw), objs, n_obj, queue, queue_cap, counters);
+        seed_phase(reinterpret_cast<float*>(smem_raw), objs, n_obj, queue, queue_cap, counters, rank, world);
         if (SELF)
         {
             // self-collision: every object against itself
             __syncthreads(); // the tile staging area is the warps' staging area again
             const uint32_t lane = lane_id();
             for (uint32_t i0 = (blockIdx.x * kColWarps + warp) * 32; i0 < n_obj; i0 += gridDim.x * kColWarps * 32)
-                stage_hits(e, lane, false, i0 + lane < n_obj, false, make_uint4(i0 + lane, i0 + lane, 0u, 0u),
-                           make_uint4(0, 0, 0, 0));
+                stage_hits(e, lane, false, i0 + lane < n_obj && (i0 + lane) % world == rank, false,
+                           make_uint4(i0 + lane, i0 + lane, 0u, 0u), make_uint4(0, 0, 0, 0));
             flush_queue(e, lane);
         }
     }
     const uint32_t seeded = grid_barrier(counters, 1, counters + CTR_Q_TAIL);
     stamp();
-    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded);
+    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded,
+                                     world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
     __syncthreads();
     stamp();
 
