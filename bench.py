@@ -788,24 +788,12 @@ def run_gpu_arm(args):
         rot_frames.append(torch.from_numpy(mb.m_positions.copy()).pin_memory())
     pair_host = torch.empty((max(8 * m1["pairs"], 1 << 16), 4), dtype=torch.int32).pin_memory()
 
-    # N > 1: every rank needs both position arrays, but eight ranks pulling the same 12.6 MB from host memory at once
-    # contend for it (measured: e2e 0.53 -> 0.77 ms at N = 8). The inputs cross PCIe ONCE, on rank 0, and reach the other
-    # GPUs over NVLink (one NCCL broadcast of both arrays on the frame's stream).
-    if dist is not None:
-        dev_in = torch.empty((2, V, 3), dtype=torch.float32, device=f"cuda:{dev}")
-
+    # N > 1: every rank uploads both position arrays itself (the BVH is replicated by recomputation). Eight ranks pulling
+    # 12.6 MB each from host memory contend for it (e2e 0.53 ms at N = 1, 0.77 ms at N = 8); crossing PCIe once on rank 0
+    # and broadcasting over NVLink with NCCL was measured SLOWER (0.82 ms: the collective couples the ranks every frame).
     def e2e_upload(i):
-        if dist is None:
-            tree_a.set_positions_from_host_ptr(host_a.data_ptr())
-            tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
-            return
-        with torch.cuda.stream(g.stream):
-            if rank == 0:
-                dev_in[0].copy_(host_a, non_blocking=True)
-                dev_in[1].copy_(rot_frames[i % len(rot_frames)], non_blocking=True)
-            dist.broadcast(dev_in, src=0)
-        tree_a.set_positions_from_device(dev_in[0].data_ptr())
-        tree_b.set_positions_from_device(dev_in[1].data_ptr())
+        tree_a.set_positions_from_host_ptr(host_a.data_ptr())
+        tree_b.set_positions_from_host_ptr(rot_frames[i % len(rot_frames)].data_ptr())
 
     def e2e_frame(i, upload=True, prefetch=None):
         # both uploads are enqueued first (they run on the library's copy stream); body A's build + refit overlap
