@@ -688,6 +688,25 @@ extern "C" int oibvh_debug_collide_profile(unsigned long long* out, int reset)
     }
     return (int)cudaMemcpyFromSymbol(out, g_col_prof, sizeof(g_col_prof));
 }
+// hop timeline: per tree level of side A, wall clock (ns) of the first / last node taken from the queue and of the last
+// node finished: [level][0..2]; [32][0] = start of the traversal
+__device__ unsigned long long g_col_hops[33][4];
+extern "C" int oibvh_debug_collide_hops(unsigned long long* out, int reset)
+{
+    if (reset)
+    {
+        static unsigned long long z[33][4];
+        for (int i = 0; i < 33; i++) { z[i][0] = ~0ull; z[i][1] = z[i][2] = z[i][3] = 0; }
+        return (int)cudaMemcpyToSymbol(g_col_hops, z, sizeof(z));
+    }
+    return (int)cudaMemcpyFromSymbol(out, g_col_hops, sizeof(g_col_hops));
+}
+__device__ __forceinline__ unsigned long long col_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
 #define COL_T(var) const long long var = clock64()
 #define COL_ADD(slot, val)                                                                                         \
     do                                                                                                             \
@@ -708,6 +727,11 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 #ifdef OIBVH_PROFILE
     unsigned long long prof[16] = {};
     const long long t_begin = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_col_hops[32][0] = col_gtime();
+    __shared__ unsigned long long s_hops[kColWarps][32][3];
+    s_hops[warp][lane][0] = ~0ull;
+    s_hops[warp][lane][1] = s_hops[warp][lane][2] = 0ull;
+    __syncwarp();
 #endif
     e.tail_seen = seeded;
     e.retire = 0;
@@ -820,6 +844,9 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         COL_T(t1b);
         COL_ADD(6, t1b - t1);
 
+#ifdef OIBVH_PROFILE
+        uint32_t my_level = 0xffffffffu;
+#endif
         // ---- phase 1: lane l prepares its item ----
         uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, meta2 = 0, key = 0;
         uint64_t ptrA = 0, ptrB = 0;
@@ -872,6 +899,14 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                         ((rem <= e.sh.cut_depth && e.sh.cut_depth < parent_rem) ? 1u << 11 : 0u);
             }
             atomicAdd(s_hist + min(la, 31u), 1u); // items per tree level of side A (oibvh_scene_get_round_stats)
+#ifdef OIBVH_PROFILE
+            {
+                const unsigned long long now = col_gtime();
+                atomicMin(&s_hops[warp][min(la, 31u)][0], now);
+                atomicMax(&s_hops[warp][min(la, 31u)][1], now);
+                my_level = min(la, 31u);
+            }
+#endif
         }
         COL_T(t1c);
         COL_ADD(7, t1c - t1b);
@@ -958,9 +993,19 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         flush_candidates(e, lane);
         COL_T(t5);
         COL_ADD(4, t5 - t4);
+#ifdef OIBVH_PROFILE
+        if (my_level != 0xffffffffu) atomicMax(&s_hops[warp][my_level][2], col_gtime());
+#endif
         if (lane == 0) e.retire += (uint32_t)__popc(got); // retired with the next reservation, or when out of work
     }
 #ifdef OIBVH_PROFILE
+    __syncwarp();
+    if (s_hops[warp][lane][1])
+    {
+        atomicMin(&g_col_hops[lane][0], s_hops[warp][lane][0]);
+        atomicMax(&g_col_hops[lane][1], s_hops[warp][lane][1]);
+        atomicMax(&g_col_hops[lane][2], s_hops[warp][lane][2]);
+    }
     if (lane == 0)
     {
         prof[5] = (unsigned long long)(clock64() - t_begin);

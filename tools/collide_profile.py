@@ -11,7 +11,9 @@ sc = ob.Scene(); sc.addOibvhTree(tA); sc.addOibvhTree(tB)
 for _ in range(3):
     sc.detect_async(4, 0); sc.counts()
 buf = np.zeros(16, np.uint64)
+hops = np.zeros((33, 4), np.uint64)
 ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
+ob._lib.oibvh_debug_collide_hops(hops.ctypes.data_as(ctypes.c_void_p), 1)
 sc.detect_async(4, 0); print("counts", sc.counts(), "phase cycles", sc.phase_cycles())
 ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 0)
 W = 148 * 32
@@ -19,3 +21,8 @@ names = ["window", "empty polls", "setup+tests", "push", "narrow", "total", "ful
 for i, n in enumerate(names):
     print(f"  {n:12s} {int(buf[i]) / W:10.0f} cycles per warp")
 print("  empty polls %d  batches %d  items %d  candidate flushes %d" % tuple(int(x) for x in buf[9:13]))
+ob._lib.oibvh_debug_collide_hops(hops.ctypes.data_as(ctypes.c_void_p), 0)
+t0 = int(hops[32, 0])
+for l in range(32):
+    if hops[l, 1]:
+        print(f"  level {l:2d}: first taken {int(hops[l,0])-t0:7d} ns  last taken {int(hops[l,1])-t0:7d} ns  last finished {int(hops[l,2])-t0:7d} ns")
