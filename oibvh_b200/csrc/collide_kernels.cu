@@ -1018,7 +1018,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 // ---------------------------------------------------------------------------------------------------
 // The persistent detection kernel
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t kColStageBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 128 KB
+constexpr size_t kColStageBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 64 KB
 constexpr size_t kColSmemBytes = kColStageBytes;
 // MODE: 0 = from the roots, 1 = from the roots + write the BVTT cut down, 2 = from the recorded cut (temporal
 // coherence); SELF = objects are also tested against themselves: separate instantiations, so that the options do not cost the everyday kernel registers (it runs at
