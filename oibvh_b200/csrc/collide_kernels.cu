@@ -15,8 +15,9 @@
 namespace oibvh
 {
 
-// One persistent cooperative kernel runs the whole detection: seeds -> ONE grid barrier -> queue-driven traversal with
-// the narrow phase fused in. One CTA of 1024 threads per SM.
+// One persistent cooperative kernel runs the whole detection: seeds -> queue-driven traversal with the narrow phase
+// fused in; no grid barrier anywhere (cooperative launch only guarantees that every CTA is resident, which the
+// queue's polling consumers rely on). One CTA of 512 threads per SM: the kernel needs 128 registers per thread.
 #ifndef OIBVH_COL_THREADS
 #define OIBVH_COL_THREADS 512
 #endif
@@ -70,12 +71,14 @@ __device__ __forceinline__ uint32_t queue_reserve(uint32_t* counters, uint32_t n
                                              ((unsigned long long)n << 32) | retire);
     return (uint32_t)(old >> 32);
 }
-// retire n items; true when every record ever pushed has been retired (nothing in flight, nothing can be pushed)
+// retire n items; true when every record ever pushed has been retired (nothing in flight, nothing can be pushed).
+// Seeding counts as one item in flight per CTA (a token that is never pushed: warp 0 of every CTA retires it after the
+// CTA's seeding), so the traversal needs no grid barrier between seeding and walking: finished == pushed + gridDim.x.
 __device__ __forceinline__ bool queue_retire(uint32_t* counters, uint32_t n)
 {
     const unsigned long long now =
         atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_Q_STATE), (unsigned long long)n) + n;
-    return (uint32_t)(now >> 32) == (uint32_t)now;
+    return (uint32_t)(now >> 32) + gridDim.x == (uint32_t)now;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -194,36 +197,6 @@ __device__ __forceinline__ uint32_t pair_linear(uint32_t n_obj, uint32_t i, uint
     return (uint32_t)((uint64_t)i * (2ull * n_obj - i - 1) / 2) + (j - i - 1);
 }
 
-// Grid-wide barrier on a monotonically increasing arrival counter (zeroed with the counter block before the
-// launch). `generation` counts the barriers passed so far. The kernel is launched cooperatively, so every CTA is
-// resident and the spin terminates; a bounded spin turns a would-be hang into a reported failure.
-__device__ __forceinline__ uint32_t grid_barrier(uint32_t* __restrict__ counters, uint32_t generation,
-                                                 const uint32_t* read_after)
-{
-    // returns *read_after as settled after the barrier, read ONCE per CTA and broadcast through shared memory
-    // (every warp of the chip polling the same word would serialise on one L2 slice)
-    __shared__ uint32_t s_value;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        // release-arrive / relaxed polls + one acquire fence (see grid_sync in common.cuh)
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + CTR_BARRIER) : "memory");
-        const uint32_t target = generation * gridDim.x;
-        uint32_t spins = 0;
-        while (ld_relaxed_gpu(counters + CTR_BARRIER) < target)
-        {
-            if (++spins > (1u << 26))
-            {
-                atomicOr(counters + CTR_OVERFLOW, 8u);
-                break;
-            }
-        }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        s_value = __ldcg(read_after);
-    }
-    __syncthreads();
-    return s_value;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Narrow phase: separating-axis test, literal operation order of the reference CPU code, IEEE fp32 with
@@ -721,7 +694,7 @@ __device__ __forceinline__ unsigned long long col_gtime()
 template <bool RECORD, bool SELF>
 __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, volatile uint32_t* s_ctl,
                                uint32_t levels0, uint32_t levels, uint32_t rank, uint32_t world, uint32_t n_obj,
-                               uint32_t seeded, bool shard_roots)
+                               bool shard_roots)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 #ifdef OIBVH_PROFILE
@@ -733,8 +706,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
     s_hops[warp][lane][1] = s_hops[warp][lane][2] = 0ull;
     __syncwarp();
 #endif
-    e.tail_seen = seeded;
-    e.retire = 0;
+    e.tail_seen = 0;
+    e.retire = warp == 0 ? 1u : 0u; // the CTA's seeding token (queue_retire)
     const uint32_t total_warps = gridDim.x * kColWarps;
     uint32_t* const ctr = e.sh.counters;
     // Slots are owned statically, round-robin: global warp w owns slots w, w + W, w + 2 W, ... (W = warps of the grid).
@@ -751,14 +724,16 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         // as possible: 32 idle warps per SM in a fat polling loop eat the issue slots of the warps that have work
         // (measured: every phase of the traversal 3-5x slower); the other lanes wait at the shuffle below. ----
         uint32_t state = 0; // 0 = a record is there, 1 = the traversal is over
+        uint4 it = make_uint4(kQEmpty, 0, 0, 0); // lane 0: the record it has been waiting for (one L2 round trip: the
+                                                 // poll that finds the record IS its fetch)
         if (lane == 0)
         {
             const uint64_t slot0 = (uint64_t)gw + (uint64_t)next * total_warps;
             if (slot0 < e.sh.queue_cap)
             {
-                const uint32_t* first = reinterpret_cast<const uint32_t*>(e.sh.queue + (uint32_t)slot0);
+                const uint4* first = e.sh.queue + (uint32_t)slot0;
                 uint32_t spins = 0;
-                while (ld_relaxed_gpu(first) == kQEmpty)
+                while ((it = ld_rec(first)).x == kQEmpty)
                 {
                     if ((++spins & 3u) != 0) continue;
                     COL_ADD(9, 4);
@@ -832,8 +807,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         if (lane == 0) window = min(32u, max(1u, 2u * max(e.tail_seen, ctl_load(s_ctl + 1)) / total_warps));
         window = __shfl_sync(0xffffffffu, window, 0);
         const uint64_t slot64 = (uint64_t)gw + (uint64_t)(next + lane) * total_warps;
-        uint4 it = make_uint4(kQEmpty, 0, 0, 0);
-        if (lane < window && slot64 < e.sh.queue_cap) it = ld_rec(e.sh.queue + (uint32_t)slot64);
+        if (lane != 0 && lane < window && slot64 < e.sh.queue_cap) it = ld_rec(e.sh.queue + (uint32_t)slot64);
         const uint32_t filled = __ballot_sync(0xffffffffu, it.x != kQEmpty);
         const uint32_t take = filled == 0xffffffffu ? 32u : (uint32_t)__ffs(~filled) - 1u; // >= 1: lane 0 saw its record
         const bool valid = lane < take;
@@ -1133,10 +1107,12 @@ __global__ void __launch_bounds__(kColThreads, 1)
             flush_queue(e, lane);
         }
     }
-    const uint32_t seeded = grid_barrier(counters, 1, counters + CTR_Q_TAIL);
+    // No grid barrier here: a warp that has nothing (more) to seed starts consuming what the others have pushed; the
+    // CTA's seeding token keeps the traversal from being declared over while anybody is still seeding.
+    __syncthreads();
     stamp();
-    if (seeded != 0 && !(__ldcg(counters + CTR_Q_STOP))) traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj, seeded,
-                                     world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
+    traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj,
+                                 world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
     __syncthreads();
     stamp();
 

@@ -106,7 +106,7 @@ enum
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
     CTR_OVERFLOW = 2, // bit 0: work queue, bit 1: cut buffer, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out
-    CTR_BARRIER = 3,  // arrival counter of the grid barrier
+    CTR_BARRIER = 3,  // (unused since the seeding barrier was removed; kept so that the layout is stable)
     CTR_CUT = 4,      // records written by a recording detection (temporal coherence)
     CTR_FRONT0 = 8,   // CTR_FRONT0 + l = BVTT nodes processed whose side-A node is at tree level l (statistics)
     CTR_MAX_ROUNDS = 32,
