@@ -700,6 +700,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 #ifdef OIBVH_PROFILE
     unsigned long long prof[16] = {};
     const long long t_begin = clock64();
+#endif
+#ifdef OIBVH_PROFILE_HOPS
     if (threadIdx.x == 0 && blockIdx.x == 0) g_col_hops[32][0] = col_gtime();
     __shared__ unsigned long long s_hops[kColWarps][32][3];
     s_hops[warp][lane][0] = ~0ull;
@@ -818,7 +820,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         COL_T(t1b);
         COL_ADD(6, t1b - t1);
 
-#ifdef OIBVH_PROFILE
+#ifdef OIBVH_PROFILE_HOPS
         uint32_t my_level = 0xffffffffu;
 #endif
         // ---- phase 1: lane l prepares its item ----
@@ -873,7 +875,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                         ((rem <= e.sh.cut_depth && e.sh.cut_depth < parent_rem) ? 1u << 11 : 0u);
             }
             atomicAdd(s_hist + min(la, 31u), 1u); // items per tree level of side A (oibvh_scene_get_round_stats)
-#ifdef OIBVH_PROFILE
+#ifdef OIBVH_PROFILE_HOPS
             {
                 const unsigned long long now = col_gtime();
                 atomicMin(&s_hops[warp][min(la, 31u)][0], now);
@@ -888,6 +890,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         for (uint32_t todo = __ballot_sync(0xffffffffu, work); todo; todo &= todo - 1)
         {
             const int k = __ffs(todo) - 1;
+            COL_T(p2s);
             const uint32_t mk = __shfl_sync(0xffffffffu, meta, k);
             const uint32_t combos = mk & 0x7ffu, nB = (mk >> 11) & 63u, db = (mk >> 17) & 7u;
             const bool to_cand = (mk >> 21) & 1u, sharded = (mk >> 22) & 1u;
@@ -898,6 +901,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
             const uint32_t zak = __shfl_sync(0xffffffffu, za, k), zbk = __shfl_sync(0xffffffffu, zb, k);
             const uint32_t kk = __shfl_sync(0xffffffffu, key, k);
             const bool self = SELF && exk == eyk;
+            COL_T(p2a);
+            COL_ADD(14, (p2a - p2s) + (long long)(self & 0));
             for (uint32_t g0 = 0; g0 < combos; g0 += 64) // warp-uniform
             {
                 const uint32_t c0 = g0 + lane, c1 = c0 + 32;
@@ -944,6 +949,13 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                 }
                 if (hit0) hit0 = box_overlap(a0, b0);
                 if (hit1) hit1 = box_overlap(a1, b1);
+#ifdef OIBVH_PROFILE
+                {
+                    const uint32_t any = __ballot_sync(0xffffffffu, hit0 || hit1); // forces the loads to complete
+                    COL_T(p2b);
+                    COL_ADD(13, (p2b - p2a) + (any & 0));
+                }
+#endif
                 if (RECORD)
                 {
                     const uint32_t m2 = __shfl_sync(0xffffffffu, meta2, k);
@@ -967,12 +979,13 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         flush_candidates(e, lane);
         COL_T(t5);
         COL_ADD(4, t5 - t4);
-#ifdef OIBVH_PROFILE
+#ifdef OIBVH_PROFILE_HOPS
         if (my_level != 0xffffffffu) atomicMax(&s_hops[warp][my_level][2], col_gtime());
 #endif
         if (lane == 0) e.retire += (uint32_t)__popc(got); // retired with the next reservation, or when out of work
     }
 #ifdef OIBVH_PROFILE
+#ifdef OIBVH_PROFILE_HOPS
     __syncwarp();
     if (s_hops[warp][lane][1])
     {
@@ -980,6 +993,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         atomicMax(&g_col_hops[lane][1], s_hops[warp][lane][1]);
         atomicMax(&g_col_hops[lane][2], s_hops[warp][lane][2]);
     }
+#endif
     if (lane == 0)
     {
         prof[5] = (unsigned long long)(clock64() - t_begin);

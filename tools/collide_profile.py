@@ -21,8 +21,11 @@ names = ["window", "empty polls", "setup+tests", "push", "narrow", "total", "ful
 for i, n in enumerate(names):
     print(f"  {n:12s} {int(buf[i]) / W:10.0f} cycles per warp")
 print("  empty polls %d  batches %d  items %d  candidate flushes %d" % tuple(int(x) for x in buf[9:13]))
+items = max(1, int(buf[11]))
+print("  phase 2 per item: parameter shuffles %.0f cycles, box loads + tests %.0f cycles; set-up+tests+staging in all %.0f per item, %.0f per batch"
+      % (int(buf[14]) / items, int(buf[13]) / items, int(buf[2]) / items, int(buf[2]) / max(1, int(buf[10]))))
 ob._lib.oibvh_debug_collide_hops(hops.ctypes.data_as(ctypes.c_void_p), 0)
 t0 = int(hops[32, 0])
 for l in range(32):
-    if hops[l, 1]:
+    if hops[l, 1] and t0:  # hop timeline: only in a -DOIBVH_PROFILE_HOPS build (it perturbs the cycle counts above)
         print(f"  level {l:2d}: first taken {int(hops[l,0])-t0:7d} ns  last taken {int(hops[l,1])-t0:7d} ns  last finished {int(hops[l,2])-t0:7d} ns")
