@@ -327,11 +327,12 @@ struct Emit
 {
     const EmitShared& sh;
     uint4* stage;                // this warp's staging: [0, kHalf) queue records, [kHalf, 2 kHalf) candidates
+    uint4* params;               // this warp's item parameters: 4 x 32 uint4, [q][item] (traverse_queue)
     uint32_t staged_f, staged_c; // warp-uniform
     uint32_t retire;             // finished items not yet retired (lane 0)
     uint32_t tail_seen;          // latest queue tail this warp has seen (lane 0): sizes its next claim
     __device__ __forceinline__ Emit(const EmitShared& s, uint4* st)
-        : sh(s), stage(st), staged_f(0), staged_c(0), retire(0), tail_seen(0)
+        : sh(s), stage(st), params(nullptr), staged_f(0), staged_c(0), retire(0), tail_seen(0)
     {
     }
 };
@@ -824,11 +825,13 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         uint32_t my_level = 0xffffffffu;
 #endif
         // ---- phase 1: lane l prepares its item ----
-        uint32_t ex = 0, ey = 0, za = 0, zb = 0, baseA = 0, baseB = 0, meta = 0, meta2 = 0, key = 0;
-        uint64_t ptrA = 0, ptrB = 0;
-        bool work = false;
+        // The item's parameters go to the warp's parameter block in shared memory ([q][item], 16-byte columns: the
+        // stores are conflict-free and phase 2 reads item k's four columns as broadcasts). Keeping them in registers and
+        // broadcasting them with ten shuffles per item cost 13 registers through the whole of phase 2 and ~300 cycles
+        // per item.
         if (valid)
         {
+            uint32_t meta2 = 0;
             const ObjDesc A = get_obj(e.sh.s_objs, e.sh.objs, it.x), B = get_obj(e.sh.s_objs, e.sh.objs, it.y);
             const LevelView va = level_view(s_lv, it.x, A), vb = level_view(s_lv, it.y, B);
             const uint32_t la = it.z >> kNodeLevelShift, pa = it.z & kNodePosMask;
@@ -843,11 +846,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
             const uint32_t nB = min(1u << db, vb.count(lcb) - fb);
             const uint32_t combos = nA * nB; // <= 1024
             const bool to_cand = (lca == A.L) && (lcb == B.L);
-            work = true;
-            ptrA = (uint64_t)A.nodes;
-            ptrB = (uint64_t)B.nodes;
-            baseA = va.offset(lca) + fa;
-            baseB = vb.offset(lcb) + fb;
+            const uint64_t ptrA = (uint64_t)A.nodes, ptrB = (uint64_t)B.nodes;
+            const uint32_t baseA = va.offset(lca) + fa, baseB = vb.offset(lcb) + fb;
             // Start fetching the two runs of descendant boxes NOW, for all the items of the batch at once (the lanes
             // set their items up in parallel): phase 2 walks the items one after the other, and without this every
             // item would wait its own L2 round trip. No register is held.
@@ -857,15 +857,13 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                 for (uint32_t o = 0; o < 24u * nA + 127u; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + o));
                 for (uint32_t o = 0; o < 24u * nB + 127u; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + o));
             }
-            ex = it.x;
-            ey = it.y;
             // emitted node ids are za + ia / zb + ib (fa, fb have their low da / db bits clear)
-            za = to_cand ? fa : ((lca << kNodeLevelShift) | fa);
-            zb = to_cand ? fb : ((lcb << kNodeLevelShift) | fb);
-            meta = combos | (nB << 11) | (db << 17) | ((nB == (1u << db)) ? 1u << 20 : 0u) | (to_cand ? 1u << 21 : 0u) |
+            const uint32_t za = to_cand ? fa : ((lca << kNodeLevelShift) | fa);
+            const uint32_t zb = to_cand ? fb : ((lcb << kNodeLevelShift) | fb);
+            const uint32_t meta = combos | (nB << 11) | (db << 17) | ((nB == (1u << db)) ? 1u << 20 : 0u) | (to_cand ? 1u << 21 : 0u) |
                    ((root && shard_roots) ? 1u << 22 : 0u);
             // the children of a root pair are dealt round-robin to the shards, keyed by the pair's linear index
-            key = pair_linear(n_obj, it.x, it.y);
+            const uint32_t key = pair_linear(n_obj, it.x, it.y);
             // recording: levels of the children, and whether their misses / hits belong to the cut (depth above the
             // leaves before and after this hop)
             if (RECORD)
@@ -874,6 +872,10 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                 meta2 = lca | (lcb << 5) | ((parent_rem > e.sh.cut_depth) ? 1u << 10 : 0u) |
                         ((rem <= e.sh.cut_depth && e.sh.cut_depth < parent_rem) ? 1u << 11 : 0u);
             }
+            e.params[lane] = make_uint4(meta, key, it.x, it.y);
+            e.params[32 + lane] = make_uint4(za, zb, baseA, baseB);
+            e.params[64 + lane] = make_uint4((uint32_t)ptrA, (uint32_t)(ptrA >> 32), (uint32_t)ptrB, (uint32_t)(ptrB >> 32));
+            if (RECORD) e.params[96 + lane].x = meta2;
             atomicAdd(s_hist + min(la, 31u), 1u); // items per tree level of side A (oibvh_scene_get_round_stats)
 #ifdef OIBVH_PROFILE_HOPS
             {
@@ -887,19 +889,20 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         COL_T(t1c);
         COL_ADD(7, t1c - t1b);
         // ---- phase 2: the warp walks the prepared items, 64 descendant pairs per step ----
-        for (uint32_t todo = __ballot_sync(0xffffffffu, work); todo; todo &= todo - 1)
+        __syncwarp();
+        for (uint32_t k = 0; k < take; k++)
         {
-            const int k = __ffs(todo) - 1;
             COL_T(p2s);
-            const uint32_t mk = __shfl_sync(0xffffffffu, meta, k);
+            const uint4 q0 = e.params[k], q1 = e.params[32 + k], q2 = e.params[64 + k];
+            const uint32_t mk = q0.x;
             const uint32_t combos = mk & 0x7ffu, nB = (mk >> 11) & 63u, db = (mk >> 17) & 7u;
             const bool to_cand = (mk >> 21) & 1u, sharded = (mk >> 22) & 1u;
-            const float2* nodesA = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrA, k));
-            const float2* nodesB = reinterpret_cast<const float2*>(__shfl_sync(0xffffffffu, ptrB, k));
-            const uint32_t bA = __shfl_sync(0xffffffffu, baseA, k), bB = __shfl_sync(0xffffffffu, baseB, k);
-            const uint32_t exk = __shfl_sync(0xffffffffu, ex, k), eyk = __shfl_sync(0xffffffffu, ey, k);
-            const uint32_t zak = __shfl_sync(0xffffffffu, za, k), zbk = __shfl_sync(0xffffffffu, zb, k);
-            const uint32_t kk = __shfl_sync(0xffffffffu, key, k);
+            const float2* nodesA = reinterpret_cast<const float2*>(((uint64_t)q2.y << 32) | q2.x);
+            const float2* nodesB = reinterpret_cast<const float2*>(((uint64_t)q2.w << 32) | q2.z);
+            const uint32_t bA = q1.z, bB = q1.w;
+            const uint32_t exk = q0.z, eyk = q0.w;
+            const uint32_t zak = q1.x, zbk = q1.y;
+            const uint32_t kk = q0.y;
             const bool self = SELF && exk == eyk;
             COL_T(p2a);
             COL_ADD(14, (p2a - p2s) + (long long)(self & 0));
@@ -958,7 +961,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 #endif
                 if (RECORD)
                 {
-                    const uint32_t m2 = __shfl_sync(0xffffffffu, meta2, k);
+                    const uint32_t m2 = e.params[96 + k].x;
                     const uint32_t la_c = (m2 & 31u) << kNodeLevelShift, lb_c = ((m2 >> 5) & 31u) << kNodeLevelShift;
                     const uint32_t pa0 = (zak & kNodePosMask) + ia0, pb0 = (zbk & kNodePosMask) + ib0;
                     const uint32_t pa1 = (zak & kNodePosMask) + ia1, pb1 = (zbk & kNodePosMask) + ib1;
@@ -1007,7 +1010,8 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 // The persistent detection kernel
 // ---------------------------------------------------------------------------------------------------
 constexpr size_t kColStageBytes = (size_t)kColWarps * kStageCap * sizeof(uint4); // 64 KB
-constexpr size_t kColSmemBytes = kColStageBytes;
+constexpr size_t kColParamBytes = (size_t)kColWarps * 4 * 32 * sizeof(uint4); // 2 KB per warp
+constexpr size_t kColSmemBytes = kColStageBytes + kColParamBytes;
 // MODE: 0 = from the roots, 1 = from the roots + write the BVTT cut down, 2 = from the recorded cut (temporal
 // coherence); SELF = objects are also tested against themselves: separate instantiations, so that the options do not cost the everyday kernel registers (it runs at
 // the 128-register cap without spilling; with the options compiled in it spilled and lost 10 %)
@@ -1095,6 +1099,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
 
     const uint32_t warp = threadIdx.x >> 5;
     Emit e(s_emit, s_stage + warp * kStageCap);
+    e.params = reinterpret_cast<uint4*>(smem_raw + kColStageBytes) + (size_t)warp * 4 * 32;
 
     // ---- seeds: queue records for the object pairs whose root boxes overlap ----
     // few pairs (the common two-body scene): every node pair of a deep level tested densely, or the root pairs
