@@ -191,28 +191,48 @@ __global__ void __launch_bounds__(kLsdThreads, 2) lsd_sort_kernel(const LsdJobs 
         uint32_t rank2[(K + 1) / 2]; // two 16-bit ranks per register
 #pragma unroll
         for (int j = 0; j < (K + 1) / 2; j++) rank2[j] = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++)
+        if (full && ipt == (uint32_t)K)
         {
-            if ((uint32_t)j < ipt && warp_base + j * 32 < T) // warp-uniform: rounds wholly past the end are skipped
+            // every slot of the CTA holds a key (all CTAs but the last of a job): no per-round bounds checks, no valid
+            // mask -- straight-line code, ~20 % fewer instructions in the phase that is issue-bound
+#pragma unroll
+            for (int j = 0; j < K; j++)
             {
                 const uint32_t d = (key[j] >> shift) & MASK;
-                uint32_t vm = 0xffffffffu;
-                bool valid = true;
-                if (!full)
-                {
-                    valid = warp_base + j * 32 + lane < T;
-                    vm = __ballot_sync(0xffffffffu, valid);
-                }
-                const uint32_t peers = digit_peers<BITS>(d, vm);
+                const uint32_t peers = digit_peers<BITS>(d, 0xffffffffu);
                 const uint32_t lower = __popc(peers & lanemask_lt());
-                // every lane reads the running count of its digit (peers read the same word: broadcast), then the
-                // lowest peer bumps it
                 const uint32_t before = my_tab[d];
                 __syncwarp();
-                if (valid && lower == 0) my_tab[d] = (uint16_t)(before + __popc(peers));
+                if (lower == 0) my_tab[d] = (uint16_t)(before + __popc(peers));
                 rank2[j >> 1] |= (before + lower) << (16 * (j & 1));
                 __syncwarp();
+            }
+        }
+        else
+        {
+    #pragma unroll
+            for (int j = 0; j < K; j++)
+            {
+                if ((uint32_t)j < ipt && warp_base + j * 32 < T) // warp-uniform: rounds wholly past the end are skipped
+                {
+                    const uint32_t d = (key[j] >> shift) & MASK;
+                    uint32_t vm = 0xffffffffu;
+                    bool valid = true;
+                    if (!full)
+                    {
+                        valid = warp_base + j * 32 + lane < T;
+                        vm = __ballot_sync(0xffffffffu, valid);
+                    }
+                    const uint32_t peers = digit_peers<BITS>(d, vm);
+                    const uint32_t lower = __popc(peers & lanemask_lt());
+                    // every lane reads the running count of its digit (peers read the same word: broadcast), then the
+                    // lowest peer bumps it
+                    const uint32_t before = my_tab[d];
+                    __syncwarp();
+                    if (valid && lower == 0) my_tab[d] = (uint16_t)(before + __popc(peers));
+                    rank2[j >> 1] |= (before + lower) << (16 * (j & 1));
+                    __syncwarp();
+                }
             }
         }
         // values are fetched now (registers were free during ranking) and used after the digit scan below, which
