@@ -972,6 +972,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                            make_uint4(exk, eyk, zak + ia1, zbk + ib1));
             }
         }
+        __syncwarp(); // the parameter block is rewritten by the next batch's phase 1
         // ---- the batch is finished only when everything it produced has left the warp ----
         COL_T(t3);
         COL_ADD(2, t3 - t1b);
