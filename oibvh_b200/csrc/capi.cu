@@ -170,6 +170,7 @@ struct oibvh_scene
     bool coherent = false;       // temporal coherence: detections start from a recorded BVTT cut while it is valid
     uint32_t cut_depth = 6;      // the cut lies this many levels above the leaves
     uint4* cut = nullptr;        // cand_cap records
+    uint4* cand = nullptr;       // candidate list, cand_cap records
     bool cut_valid = false;
     uint32_t last_mode = 0;      // mode of the last enqueued detection (0 plain, 1 recording, 2 from the cut)
     std::vector<uint64_t> cut_sig; // what the cut was recorded on: scene set-up + the build serial of every tree
@@ -337,7 +338,8 @@ void scene_free_buffers(oibvh_scene* s)
     cudaFree(s->queue);
     cudaFree(s->pair_block);
     cudaFree(s->cut);
-    s->cut = nullptr;
+    cudaFree(s->cand);
+    s->cut = s->cand = nullptr;
     s->cut_valid = false;
     s->queue = s->pairs = s->pair_block = nullptr;
     s->counters = s->counters_own;
@@ -350,13 +352,15 @@ int scene_alloc_buffers(oibvh_scene* s, uint32_t front_cap, uint32_t cand_cap, u
     int rc;
     static_assert(CTR_WORDS * sizeof(uint32_t) % sizeof(uint4) == 0, "the counter block is a whole number of records");
     constexpr size_t kCtrRecords = CTR_WORDS * sizeof(uint32_t) / sizeof(uint4);
-    // (candidates are tested by the warp that finds them and never stored: cand_cap sizes the BVTT cut of a scene
-    // with temporal coherence instead)
+    // (cand_cap sizes the candidate list and, for a scene with temporal coherence, the BVTT cut)
     if ((rc = dev_alloc(&s->queue, front_cap)) || (rc = dev_alloc(&s->pair_block, kCtrRecords + (size_t)pair_cap)) ||
+        (rc = dev_alloc(&s->cand, cand_cap)) ||
         (s->coherent && (rc = dev_alloc(&s->cut, cand_cap))))
         return rc;
     {
         cudaError_t e = cudaMemsetAsync(s->queue, 0xff, sizeof(uint4) * (size_t)front_cap, s->ctx->stream);
+        // (the candidate list uses the same empty marker)
+        if (e == cudaSuccess) e = cudaMemsetAsync(s->cand, 0xff, sizeof(uint4) * (size_t)cand_cap, s->ctx->stream);
         if (e != cudaSuccess) return fail(OIBVH_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
     }
     s->counters = reinterpret_cast<uint32_t*>(s->pair_block);
@@ -1599,6 +1603,8 @@ static int scene_enqueue(oibvh_scene* s, uint32_t entry_level, uint32_t expand_l
     opt.self = s->self_collision ? 1u : 0u;
     opt.cut = s->cut;
     opt.cut_cap = s->cand_cap;
+    opt.cand = s->cand;
+    opt.cand_cap = s->cand_cap;
     opt.cut_depth = s->cut_depth;
     opt.cut_state = s->mg_state + MG_CUT;
     const uint64_t n_pairs = (uint64_t)n_obj * (n_obj - 1) / 2 + (s->self_collision ? n_obj : 0);
@@ -1878,13 +1884,17 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         {
             // the queue may hold stale records: put the empty marker back before anything else runs on it
             if (scene->queue) cudaMemsetAsync(scene->queue, 0xff, sizeof(uint4) * (size_t)scene->front_cap, ctx->stream);
+            if (scene->cand) cudaMemsetAsync(scene->cand, 0xff, sizeof(uint4) * (size_t)scene->cand_cap, ctx->stream);
             return fail(OIBVH_ERR_INTERNAL, "a wait timed out in the detection kernel");
         }
         if (h[CTR_OVERFLOW] & 16u)
             return fail(OIBVH_ERR_INTERNAL, "multi-GPU detection: a rank did not open / finish the frame in time");
         if (h[CTR_OVERFLOW] != 0 && scene->queue)
+        {
             // an aborted traversal leaves records in the queue: restore the empty marker (regrowing does it too)
             CU(cudaMemsetAsync(scene->queue, 0xff, sizeof(uint4) * (size_t)scene->front_cap, ctx->stream));
+            CU(cudaMemsetAsync(scene->cand, 0xff, sizeof(uint4) * (size_t)scene->cand_cap, ctx->stream));
+        }
         if (h[CTR_OVERFLOW] != 0 && scene->mg_mode != 0)
             return fail(OIBVH_ERR_OVERFLOW, "multi-GPU detection: a work queue overflowed (flags %u); the queues of a "
                                             "multi-GPU scene are fixed -- oibvh_scene_reserve before oibvh_mgpu_export",
@@ -1900,6 +1910,7 @@ extern "C" int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uin
         scene->cut_valid = false; // a detection that overflowed has not recorded a complete cut
         if (h[CTR_OVERFLOW] & 1u) fc = grow_to(fc, max_front); // every BVTT node of the traversal passes through the queue
         if (h[CTR_OVERFLOW] & 2u) cc = grow_to(cc, h[CTR_CUT]);
+        if (h[CTR_OVERFLOW] & 32u) cc = grow_to(cc, h[CTR_CAND_TAIL]);
         if (h[CTR_OVERFLOW] & 4u) pc = grow_to(pc, h[CTR_PAIRS]);
         if (fc == scene->front_cap && cc == scene->cand_cap && pc == scene->pair_cap)
             return fail(OIBVH_ERR_OVERFLOW, "work queues cannot grow further");

@@ -19,7 +19,7 @@ namespace oibvh
 // fused in; no grid barrier anywhere (cooperative launch only guarantees that every CTA is resident, which the
 // queue's polling consumers rely on). One CTA of 512 threads per SM: the kernel needs 128 registers per thread.
 #ifndef OIBVH_COL_THREADS
-#define OIBVH_COL_THREADS 512
+#define OIBVH_COL_THREADS 768
 #endif
 constexpr int kColThreads = OIBVH_COL_THREADS;
 constexpr int kColWarps = kColThreads / 32;
@@ -321,6 +321,8 @@ struct EmitShared
     uint4* cut;
     uint32_t cut_cap;
     uint32_t cut_depth;  // levels above the leaves at which the cut lies
+    uint4* cand;         // candidate list (leaf pairs with overlapping boxes): narrow_owned_blocks
+    uint32_t cand_cap;
     ObjDesc s_objs[kObjCache];
 };
 struct Emit
@@ -330,9 +332,10 @@ struct Emit
     uint4* params;               // this warp's item parameters: 4 x 32 uint4, [q][item] (traverse_queue)
     uint32_t staged_f, staged_c; // warp-uniform
     uint32_t retire;             // finished items not yet retired (lane 0)
+    uint32_t cand_next;          // candidate blocks of this warp already tested (warp-uniform)
     uint32_t tail_seen;          // latest queue tail this warp has seen (lane 0): sizes its next claim
     __device__ __forceinline__ Emit(const EmitShared& s, uint4* st)
-        : sh(s), stage(st), params(nullptr), staged_f(0), staged_c(0), retire(0), tail_seen(0)
+        : sh(s), stage(st), params(nullptr), staged_f(0), staged_c(0), retire(0), cand_next(0), tail_seen(0)
     {
     }
 };
@@ -344,63 +347,110 @@ struct Emit
 #ifndef OIBVH_SAT_INLINE
 #define OIBVH_SAT_INLINE __noinline__
 #endif
-__device__ OIBVH_SAT_INLINE void narrow_staged(const EmitShared& sh, const uint4* src, uint32_t n, uint32_t lane)
+__device__ OIBVH_SAT_INLINE void narrow_lanes(const EmitShared& sh, uint4 c, bool valid, uint32_t lane)
 {
-    for (uint32_t base = 0; base < n; base += 32)
+    bool hit = false;
+    if (valid)
     {
-        const uint32_t i = base + lane;
-        bool hit = false;
-        uint4 c = make_uint4(0, 0, 0, 0);
-        if (i < n)
+        const ObjDesc A = get_obj(sh.s_objs, sh.objs, c.x), B = get_obj(sh.s_objs, sh.objs, c.y);
+        const uint32_t* fa = A.faces + 3ull * c.z;
+        const uint32_t* fb = B.faces + 3ull * c.w;
+        const uint32_t a0 = __ldg(fa), a1 = __ldg(fa + 1), a2 = __ldg(fa + 2);
+        const uint32_t b0 = __ldg(fb), b1 = __ldg(fb + 1), b2 = __ldg(fb + 2);
+        // self-collision: two triangles of ONE mesh that share a vertex always touch there -- they are neighbours,
+        // not a collision (decided before the test so that the six indices are dead during it)
+        const bool neighbours = c.x == c.y && (a0 == b0 || a0 == b1 || a0 == b2 || a1 == b0 || a1 == b1 || a1 == b2 ||
+                                               a2 == b0 || a2 == b1 || a2 == b2);
+        const V3 P1 = load_v3(A.pos, a0), P2 = load_v3(A.pos, a1), P3 = load_v3(A.pos, a2);
+        const V3 Q1 = load_v3(B.pos, b0), Q2 = load_v3(B.pos, b1), Q3 = load_v3(B.pos, b2);
+        hit = !neighbours && triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (mask)
+    {
+        uint32_t slot = 0;
+        if (lane == 0)
         {
-            c = src[i];
-            const ObjDesc A = get_obj(sh.s_objs, sh.objs, c.x), B = get_obj(sh.s_objs, sh.objs, c.y);
-            const uint32_t* fa = A.faces + 3ull * c.z;
-            const uint32_t* fb = B.faces + 3ull * c.w;
-            const uint32_t a0 = __ldg(fa), a1 = __ldg(fa + 1), a2 = __ldg(fa + 2);
-            const uint32_t b0 = __ldg(fb), b1 = __ldg(fb + 1), b2 = __ldg(fb + 2);
-            // self-collision: two triangles of ONE mesh that share a vertex always touch there -- they are neighbours,
-            // not a collision (decided before the test so that the six indices are dead during it)
-            const bool neighbours = c.x == c.y && (a0 == b0 || a0 == b1 || a0 == b2 || a1 == b0 || a1 == b1 || a1 == b2 ||
-                                                   a2 == b0 || a2 == b1 || a2 == b2);
-            const V3 P1 = load_v3(A.pos, a0), P2 = load_v3(A.pos, a1), P3 = load_v3(A.pos, a2);
-            const V3 Q1 = load_v3(B.pos, b0), Q2 = load_v3(B.pos, b1), Q3 = load_v3(B.pos, b2);
-            hit = !neighbours && triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
+            if (sh.remote)
+            {
+                atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask)); // this rank's own count
+                slot = atomicAdd_system(sh.pair_ctr + CTR_PAIRS, (uint32_t)__popc(mask));
+            }
+            else
+                slot = atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask));
         }
-        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        if (mask)
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (hit)
         {
-            uint32_t slot = 0;
-            if (lane == 0)
-            {
-                if (sh.remote)
-                {
-                    atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask)); // this rank's own count
-                    slot = atomicAdd_system(sh.pair_ctr + CTR_PAIRS, (uint32_t)__popc(mask));
-                }
-                else
-                    slot = atomicAdd(sh.counters + CTR_PAIRS, (uint32_t)__popc(mask));
-            }
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (hit)
-            {
-                const uint32_t dst = slot + __popc(mask & lanemask_lt());
-                if (dst < sh.pair_cap)
-                    sh.pairs[dst] = c; // {bvhA, bvhB, triA, triB} == int_tri_pair_node_t
-                else if (sh.remote)
-                    atomicOr_system(sh.pair_ctr + CTR_OVERFLOW, 4u);
-                else
-                    atomicOr(sh.counters + CTR_OVERFLOW, 4u);
-            }
+            const uint32_t dst = slot + __popc(mask & lanemask_lt());
+            if (dst < sh.pair_cap)
+                sh.pairs[dst] = c; // {bvhA, bvhB, triA, triB} == int_tri_pair_node_t
+            else if (sh.remote)
+                atomicOr_system(sh.pair_ctr + CTR_OVERFLOW, 4u);
+            else
+                atomicOr(sh.counters + CTR_OVERFLOW, 4u);
         }
     }
+    const uint32_t n = __popc(__ballot_sync(0xffffffffu, valid));
     if (lane == 0) atomicAdd(sh.counters + CTR_CANDIDATES, n);
 }
+
+// The candidate list is cut into blocks of kCandBlock records that the warps own round-robin (block b belongs to global
+// warp b mod W), like the slots of the work queue: no claim atomics, and every warp gets its share whatever the size of
+// the list. A warp tests up to four of its blocks at once (a lane per candidate). It does so (a) whenever it has been
+// waiting for work for a while during the traversal -- the triangle tests then run under the traversal instead of after
+// it -- and (b) for what is left once the traversal is over. A block is ready when the list's tail has passed it; a
+// record that has been reserved but not yet written still holds the empty marker (single-copy-atomic 128-bit records,
+// as in the queue) and is waited for. A consumed record is set back to the empty marker by its consumer, so the kernel
+// leaves the list empty for the next launch.
+constexpr uint32_t kCandBlock = 8;
+__device__ __forceinline__ bool narrow_owned_blocks(const EmitShared& sh, uint32_t gw, uint32_t total_warps,
+                                                    uint32_t& cnext, uint32_t tail, bool final, uint32_t lane)
+{
+    tail = min(tail, sh.cand_cap);
+    const uint32_t j = lane / kCandBlock, i = lane % kCandBlock;
+    const uint64_t blk = (uint64_t)gw + (uint64_t)(cnext + j) * total_warps;
+    const uint64_t idx = blk * kCandBlock + i;
+    // ready: the whole block lies below the tail; at the end a partial block counts too
+    const bool block_ready = final ? blk * kCandBlock < tail : (blk + 1) * kCandBlock <= tail;
+    const uint32_t ready = __ballot_sync(0xffffffffu, block_ready && i == 0); // one bit per ready block
+    if (ready == 0) return false;
+    const bool valid = block_ready && idx < tail;
+    uint4 c = make_uint4(0, 0, 0, 0);
+    if (valid)
+    {
+        uint32_t spins = 0;
+        while ((c = ld_rec(sh.cand + idx)).x == kQEmpty && ++spins < (1u << 20)) {}
+        if (c.x == kQEmpty)
+            atomicOr(sh.counters + CTR_OVERFLOW, 8u); // the producer never wrote it: report, do not hang
+        else
+            sh.cand[idx] = make_uint4(kQEmpty, kQEmpty, kQEmpty, kQEmpty); // consumed
+    }
+    narrow_lanes(sh, c, valid && c.x != kQEmpty, lane);
+    cnext += (uint32_t)__popc(ready);
+    return true;
+}
+
+// Staged candidates go to the candidate list in global memory (narrow_owned_blocks tests them). Testing them right here,
+// by the warp that found them, was measured: the call in the middle of the traversal's state costs registers -- the
+// kernel needed 128 (16 warps per SM) and large scenes are bound by exactly that; without it the kernel fits 80 registers
+// and 24 warps per SM (4096-body scene 283 -> 245 us, terrain 171 -> 140 us; the two-body bench scene is bound by its
+// hop latencies and does not care: 47-51 us either way).
 __device__ __forceinline__ void flush_candidates(Emit& e, uint32_t lane)
 {
-    if (e.staged_c == 0) return;
+    const uint32_t n = e.staged_c;
+    if (n == 0) return;
     __syncwarp();
-    narrow_staged(e.sh, e.stage + kHalf, e.staged_c, lane);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(e.sh.counters + CTR_CAND_TAIL, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > e.sh.cand_cap && lane == 0)
+    {
+        atomicOr(e.sh.counters + CTR_OVERFLOW, 32u); // the host regrows the list and repeats the detection
+        st_relaxed_gpu(e.sh.counters + CTR_Q_STOP, 1u);
+    }
+    for (uint32_t j = lane; j < n; j += 32)
+        if (base + j < e.sh.cand_cap) st_rec(e.sh.cand + base + j, e.stage[kHalf + j]);
     __syncwarp();
     e.staged_c = 0;
 }
@@ -720,6 +770,7 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
     // several nodes per warp) and takes the filled prefix.
     const uint32_t gw = blockIdx.x * kColWarps + warp;
     uint32_t next = 0; // this warp's next slot is gw + next * W
+    uint32_t& cnext = e.cand_next; // this warp's next candidate block is gw + cnext * W (narrow_owned_blocks)
     for (;;)
     {
         COL_T(t0);
@@ -760,11 +811,20 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     if ((((uint32_t)clock64() >> 11) % kColWarps) == warp)
                     {
                         ctl_store(s_ctl + 1, ld_relaxed_gpu(ctr + CTR_Q_TAIL));
+                        ctl_store(s_ctl + 2, ld_relaxed_gpu(ctr + CTR_CAND_TAIL));
                         if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) ctl_store(s_ctl, 1u);
                     }
                     if (ctl_load(s_ctl))
                     {
                         state = 1;
+                        break;
+                    }
+                    // (3) Still nothing after a while: candidates of this warp's blocks may be waiting for their triangle
+                    //     tests (narrow_owned_blocks) -- leave the poll loop for them (state 2)
+                    if ((spins & 15u) == 0 &&
+                        ((uint64_t)gw + (uint64_t)cnext * total_warps + 1) * kCandBlock <= ctl_load(s_ctl + 2))
+                    {
+                        state = 2;
                         break;
                     }
                     if (spins > (1u << 22))
@@ -802,6 +862,17 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
         state = __shfl_sync(0xffffffffu, state, 0);
         COL_T(t1);
         COL_ADD(1, t1 - t0);
+        if (state == 2)
+        {
+            // idle: test the candidates of this warp's ready blocks, then go back to waiting for the slot
+            uint32_t ct = 0;
+            if (lane == 0) ct = ctl_load(s_ctl + 2);
+            ct = __shfl_sync(0xffffffffu, ct, 0);
+            narrow_owned_blocks(e.sh, gw, total_warps, cnext, ct, false, lane);
+            COL_T(t1n);
+            COL_ADD(4, t1n - t1);
+            continue;
+        }
         if (state) break;
         // ---- take the filled prefix of a window of this warp's next slots: one while the queue is short, up to 32
         // once there are several nodes per warp (records of different producers may become visible out of order:
@@ -1029,7 +1100,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
     ObjDesc* const s_objs = s_emit.s_objs;
     __shared__ uint32_t s_lv[kObjCache * 64]; // per cached object: off[32], cnt[32]
     __shared__ uint32_t s_hist[32];           // items per tree level (statistics)
-    __shared__ uint32_t s_ctl[2];             // CTA copy of (stop flag, queue tail), refreshed by one warp at a time
+    __shared__ uint32_t s_ctl[3];             // CTA copy of (stop flag, queue tail, candidate tail), refreshed by one warp at a time
     for (uint32_t i = threadIdx.x; i < min(n_obj, (uint32_t)kObjCache) * 32; i += blockDim.x)
     {
         const uint32_t o = i >> 5, l = i & 31u;
@@ -1041,7 +1112,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
     if (threadIdx.x < 32) s_hist[threadIdx.x] = 0u;
     if (threadIdx.x == 0)
     {
-        s_ctl[0] = s_ctl[1] = 0u;
+        s_ctl[0] = s_ctl[1] = s_ctl[2] = 0u;
         const bool remote = mg.mode == 2;
         s_emit.queue = queue;
         s_emit.queue_cap = queue_cap;
@@ -1053,6 +1124,8 @@ __global__ void __launch_bounds__(kColThreads, 1)
         s_emit.pair_ctr = remote ? mg.root_counters : counters;
         s_emit.record = RECORD ? 1u : 0u;
         s_emit.cut = opt.cut;
+        s_emit.cand = opt.cand;
+        s_emit.cand_cap = opt.cand_cap;
         s_emit.cut_cap = opt.cut_cap;
         s_emit.cut_depth = opt.cut_depth;
     }
@@ -1133,6 +1206,18 @@ __global__ void __launch_bounds__(kColThreads, 1)
     stamp();
     traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj,
                                  world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
+    __syncthreads();
+    stamp();
+
+    // ---- narrow phase, the rest: the traversal is over (everything pushed has been retired, and a warp retires a batch
+    // only after its candidates have their places in the list), so the tail is final; every warp tests what is left of
+    // its blocks, including a partial last one ----
+    {
+        const uint32_t lane = lane_id();
+        const uint32_t n_cand = ld_relaxed_gpu(counters + CTR_CAND_TAIL);
+        const uint32_t gw = blockIdx.x * kColWarps + warp;
+        while (narrow_owned_blocks(s_emit, gw, gridDim.x * kColWarps, e.cand_next, n_cand, true, lane)) {}
+    }
     __syncthreads();
     stamp();
 

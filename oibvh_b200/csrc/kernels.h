@@ -105,9 +105,11 @@ enum
 {
     CTR_CANDIDATES = 0,
     CTR_PAIRS = 1,
-    CTR_OVERFLOW = 2, // bit 0: work queue, bit 1: cut buffer, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out
+    CTR_OVERFLOW = 2, // bit 0: work queue, bit 1: cut buffer, bit 2: pairs, bit 3: a wait timed out, bit 4: multi-GPU wait timed out,
+                      // bit 5: candidate list
     CTR_BARRIER = 3,  // (unused since the seeding barrier was removed; kept so that the layout is stable)
     CTR_CUT = 4,      // records written by a recording detection (temporal coherence)
+    CTR_CAND_TAIL = 5, // candidates (leaf pairs with overlapping boxes) appended to the candidate list
     CTR_FRONT0 = 8,   // CTR_FRONT0 + l = BVTT nodes processed whose side-A node is at tree level l (statistics)
     CTR_MAX_ROUNDS = 32,
     CTR_TIME0 = 64,   // CTR_TIME0 + i = SM cycle counter (low 32 bits) of CTA 0 at phase boundary i
@@ -152,6 +154,8 @@ struct DetectOpts
     uint32_t cut_cap;
     uint32_t cut_depth;  // the cut lies this many levels above the leaves
     uint32_t* cut_state; // persistent: [0] = number of records of the recorded cut
+    uint4* cand;         // candidate list: (objA, objB, triA, triB), tested by the narrow phase after the traversal
+    uint32_t cand_cap;
 };
 // root: zero the counter block of the coming frame, then publish MG_OPEN = frame (system scope)
 cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s);
