@@ -23,6 +23,17 @@ namespace oibvh
 #endif
 constexpr int kColThreads = OIBVH_COL_THREADS;
 constexpr int kColWarps = kColThreads / 32;
+// Warp roles during the traversal: the first kTravWarps warps of a CTA walk the BVTT; one CONTROL warp keeps the CTA's
+// shared copy of the queue's control words fresh; the remaining kAuxWarps - 1 NARROW warps test candidates while the
+// traversal is still producing them. Seeding before and the rest of the narrow phase after are done by all warps.
+#ifndef OIBVH_COL_AUX_WARPS
+#define OIBVH_COL_AUX_WARPS 4
+#endif
+constexpr int kAuxWarps = OIBVH_COL_AUX_WARPS;
+constexpr int kTravWarps = kColWarps - kAuxWarps;
+constexpr int kNarrowWarps = kAuxWarps - 1;
+static_assert(kAuxWarps >= 2 && kTravWarps >= 4, "one control warp, at least one narrow warp, traversal warps");
+static_assert(kColWarps % kNarrowWarps == 0, "the narrow warps' backlog is dealt evenly to the CTA's warps");
 
 __device__ __forceinline__ ObjDesc load_obj(const ObjDesc* __restrict__ objs, uint32_t i)
 {
@@ -332,10 +343,9 @@ struct Emit
     uint4* params;               // this warp's item parameters: 4 x 32 uint4, [q][item] (traverse_queue)
     uint32_t staged_f, staged_c; // warp-uniform
     uint32_t retire;             // finished items not yet retired (lane 0)
-    uint32_t cand_next;          // candidate blocks of this warp already tested (warp-uniform)
     uint32_t tail_seen;          // latest queue tail this warp has seen (lane 0): sizes its next claim
     __device__ __forceinline__ Emit(const EmitShared& s, uint4* st)
-        : sh(s), stage(st), params(nullptr), staged_f(0), staged_c(0), retire(0), cand_next(0), tail_seen(0)
+        : sh(s), stage(st), params(nullptr), staged_f(0), staged_c(0), retire(0), tail_seen(0)
     {
     }
 };
@@ -395,43 +405,114 @@ __device__ OIBVH_SAT_INLINE void narrow_lanes(const EmitShared& sh, uint4 c, boo
     if (lane == 0) atomicAdd(sh.counters + CTR_CANDIDATES, n);
 }
 
-// The candidate list is cut into blocks of kCandBlock records that the warps own round-robin (block b belongs to global
-// warp b mod W), like the slots of the work queue: no claim atomics, and every warp gets its share whatever the size of
-// the list. A warp tests up to four of its blocks at once (a lane per candidate). It does so (a) whenever it has been
-// waiting for work for a while during the traversal -- the triangle tests then run under the traversal instead of after
-// it -- and (b) for what is left once the traversal is over. A block is ready when the list's tail has passed it; a
-// record that has been reserved but not yet written still holds the empty marker (single-copy-atomic 128-bit records,
-// as in the queue) and is waited for. A consumed record is set back to the empty marker by its consumer, so the kernel
-// leaves the list empty for the next launch.
-constexpr uint32_t kCandBlock = 8;
-__device__ __forceinline__ bool narrow_owned_blocks(const EmitShared& sh, uint32_t gw, uint32_t total_warps,
-                                                    uint32_t& cnext, uint32_t tail, bool final, uint32_t lane)
+// The CTA's copy of (stop flag, queue tail, candidate tail) is written by the control warp (and by a warp that raises the
+// stop flag) and read by all the others with no barrier in between -- single words, any interleaving is fine.
+// Shared-memory atomics make that explicit (to the reader and to racecheck); they are issued by one lane, a few times
+// per thousand cycles.
+__device__ __forceinline__ uint32_t ctl_load(volatile uint32_t* p) { return atomicOr(const_cast<uint32_t*>(p), 0u); }
+__device__ __forceinline__ void ctl_store(volatile uint32_t* p, uint32_t v) { atomicExch(const_cast<uint32_t*>(p), v); }
+
+// The candidate list is cut into groups of 32 records that the NARROW warps of the grid own round-robin (group g belongs
+// to narrow warp g mod NW), like the slots of the work queue: no claim counter. (Measured: claiming groups from one head
+// counter with compare-and-swap serialised the claims at one per L2 round trip and, sharing a cache line with the
+// counters the producers hit, slowed the traversal by a quarter.) A narrow warp tests its groups as the tail passes them;
+// what it has not reached when the traversal ends is shared out among all the warps of its CTA. A group below the tail
+// has been reserved by its producers; a record that has not been written yet still holds the empty marker
+// (single-copy-atomic 128-bit records, as in the queue) and is waited for. A consumed record is set back to the empty
+// marker by its consumer, so the kernel leaves the list empty for the next launch.
+// test the candidates [base, base + n), n <= 32, one per lane
+__device__ __forceinline__ void narrow_range(const EmitShared& sh, uint32_t base, uint32_t n, uint32_t lane)
 {
-    tail = min(tail, sh.cand_cap);
-    const uint32_t j = lane / kCandBlock, i = lane % kCandBlock;
-    const uint64_t blk = (uint64_t)gw + (uint64_t)(cnext + j) * total_warps;
-    const uint64_t idx = blk * kCandBlock + i;
-    // ready: the whole block lies below the tail; at the end a partial block counts too
-    const bool block_ready = final ? blk * kCandBlock < tail : (blk + 1) * kCandBlock <= tail;
-    const uint32_t ready = __ballot_sync(0xffffffffu, block_ready && i == 0); // one bit per ready block
-    if (ready == 0) return false;
-    const bool valid = block_ready && idx < tail;
+    const bool valid = lane < n;
     uint4 c = make_uint4(0, 0, 0, 0);
     if (valid)
     {
         uint32_t spins = 0;
-        while ((c = ld_rec(sh.cand + idx)).x == kQEmpty && ++spins < (1u << 20)) {}
+        while ((c = ld_rec(sh.cand + base + lane)).x == kQEmpty && ++spins < (1u << 20)) {}
         if (c.x == kQEmpty)
             atomicOr(sh.counters + CTR_OVERFLOW, 8u); // the producer never wrote it: report, do not hang
         else
-            sh.cand[idx] = make_uint4(kQEmpty, kQEmpty, kQEmpty, kQEmpty); // consumed
+            sh.cand[base + lane] = make_uint4(kQEmpty, kQEmpty, kQEmpty, kQEmpty); // consumed
     }
     narrow_lanes(sh, c, valid && c.x != kQEmpty, lane);
-    cnext += (uint32_t)__popc(ready);
-    return true;
+}
+// What the auxiliary warps of a CTA do while the others traverse. The CONTROL warp reads the queue's control words
+// (stop flag, queue tail, candidate tail) from global memory about once per thousand cycles and publishes them in
+// shared memory, where the CTA's other warps read them -- thousands of idle warps must not poll those words in global
+// memory, and a refresh that depends on some idle traversal warp happening to be on duty left gaps of several thousand
+// cycles. The NARROW warps test candidates as the traversal produces them, so that most of the narrow phase runs under
+// the traversal instead of after it.
+__device__ __forceinline__ void aux_loop(const EmitShared& sh, volatile uint32_t* s_ctl, uint32_t* s_backlog, uint32_t warp,
+                                         uint32_t lane)
+{
+    uint32_t* const ctr = sh.counters;
+    if (warp == (uint32_t)kTravWarps)
+    {
+        if (lane == 0)
+        {
+            uint32_t rounds = 0;
+            for (;;)
+            {
+                ctl_store(s_ctl + 1, ld_relaxed_gpu(ctr + CTR_Q_TAIL));
+                ctl_store(s_ctl + 2, ld_relaxed_gpu(ctr + CTR_CAND_TAIL));
+                if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) ctl_store(s_ctl, 1u);
+                if (ctl_load(s_ctl)) break;
+                if (++rounds > (1u << 22)) // seconds: report instead of hanging
+                {
+                    atomicOr(ctr + CTR_OVERFLOW, 8u);
+                    st_relaxed_gpu(ctr + CTR_Q_STOP, 1u);
+                    ctl_store(s_ctl, 1u);
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        __syncwarp();
+        return;
+    }
+    // narrow warp `a` of this CTA = narrow warp blockIdx.x * kNarrowWarps + a of the grid
+    const uint32_t a = warp - (uint32_t)kTravWarps - 1u;
+    const uint32_t nw = blockIdx.x * kNarrowWarps + a, NW = gridDim.x * kNarrowWarps;
+    uint32_t k = 0; // this warp's next group is nw + k * NW
+    for (;;)
+    {
+        uint32_t stop = 0, tail = 0;
+        if (lane == 0)
+        {
+            stop = ctl_load(s_ctl);
+            tail = ctl_load(s_ctl + 2);
+        }
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        tail = min(__shfl_sync(0xffffffffu, tail, 0), sh.cand_cap);
+        const uint64_t g = (uint64_t)nw + (uint64_t)k * NW;
+        if ((g + 1) * 32u <= tail)
+        {
+            narrow_range(sh, (uint32_t)(g * 32u), 32u, lane);
+            k++;
+            continue;
+        }
+        if (stop) break;
+        __nanosleep(400);
+    }
+    if (lane == 0) s_backlog[a] = k; // where the CTA's warps take over (narrow_rest)
+}
+// after the traversal: the groups the CTA's narrow warps have not reached, dealt to all of its warps
+__device__ __forceinline__ void narrow_rest(const EmitShared& sh, const uint32_t* s_backlog, uint32_t n_cand, uint32_t warp,
+                                            uint32_t lane)
+{
+    n_cand = min(n_cand, sh.cand_cap);
+    constexpr uint32_t kStep = kColWarps / kNarrowWarps;
+    const uint32_t a = warp % kNarrowWarps;
+    const uint32_t nw = blockIdx.x * kNarrowWarps + a, NW = gridDim.x * kNarrowWarps;
+    for (uint32_t k = s_backlog[a] + warp / kNarrowWarps;; k += kStep)
+    {
+        const uint64_t first = ((uint64_t)nw + (uint64_t)k * NW) * 32u;
+        if (first >= n_cand) break;
+        narrow_range(sh, (uint32_t)first, min(32u, n_cand - (uint32_t)first), lane);
+    }
 }
 
-// Staged candidates go to the candidate list in global memory (narrow_owned_blocks tests them). Testing them right here,
+// Staged candidates go to the candidate list in global memory (the narrow warps test them: aux_loop, narrow_rest). Testing them right here,
 // by the warp that found them, was measured: the call in the middle of the traversal's state costs registers -- the
 // kernel needed 128 (16 warps per SM) and large scenes are bound by exactly that; without it the kernel fits 80 registers
 // and 24 warps per SM (4096-body scene 283 -> 245 us, terrain 171 -> 140 us; the two-body bench scene is bound by its
@@ -692,12 +773,6 @@ __device__ void cut_seed_phase(Emit& e, const uint32_t* s_lv, uint32_t n_cut)
 // equal knows that nothing is in flight and nothing can be pushed any more: it raises the stop flag. The hop latency is ~4 dependent L2 round trips
 // (claim, record, boxes, push) instead of a grid barrier on top of them, and hops of different subtrees overlap.
 // ---------------------------------------------------------------------------------------------------
-// The CTA's copy of (stop flag, queue tail) is written by whichever warp is on duty and read by all the others with no
-// barrier in between -- single words, any interleaving is fine. Shared-memory atomics make that explicit (to the reader
-// and to racecheck); they are issued by one lane, a few times per thousand cycles.
-__device__ __forceinline__ uint32_t ctl_load(volatile uint32_t* p) { return atomicOr(const_cast<uint32_t*>(p), 0u); }
-__device__ __forceinline__ void ctl_store(volatile uint32_t* p, uint32_t v) { atomicExch(const_cast<uint32_t*>(p), v); }
-
 #ifdef OIBVH_PROFILE
 // where the traversal's warps spend their time (summed over all warps, lane 0's clock): [0] window, [1] polls that
 // found nothing, [2] set-up + box tests + staging, [3] queue pushes, [4] narrow phase, [5] total, [6] polls that found
@@ -761,16 +836,15 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
 #endif
     e.tail_seen = 0;
     e.retire = warp == 0 ? 1u : 0u; // the CTA's seeding token (queue_retire)
-    const uint32_t total_warps = gridDim.x * kColWarps;
+    const uint32_t total_warps = gridDim.x * kTravWarps; // traversal warps of the grid
     uint32_t* const ctr = e.sh.counters;
     // Slots are owned statically, round-robin: global warp w owns slots w, w + W, w + 2 W, ... (W = warps of the grid).
     // No head counter, no claim atomics (measured: thousands of warps claiming from one counter waited 5-7 K cycles per
     // claim -- an L2 slice serves same-address atomics a few cycles apart), and the nodes of every hop are dealt evenly
     // to the warps. A warp looks at a window of its next slots (one while the queue is short, up to 32 once there are
     // several nodes per warp) and takes the filled prefix.
-    const uint32_t gw = blockIdx.x * kColWarps + warp;
+    const uint32_t gw = blockIdx.x * kTravWarps + warp;
     uint32_t next = 0; // this warp's next slot is gw + next * W
-    uint32_t& cnext = e.cand_next; // this warp's next candidate block is gw + cnext * W (narrow_owned_blocks)
     for (;;)
     {
         COL_T(t0);
@@ -806,25 +880,11 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     }
                     // (2) Thousands of idle warps must NOT poll the stop flag and the tail in global memory: those two
                     //     words (the tail shares its line with the counter every push hits) would saturate their L2
-                    //     slice. One warp per CTA at a time -- the one whose number matches the current 2 K-cycle window
-                    //     -- refreshes a copy in shared memory; everybody else reads that.
-                    if ((((uint32_t)clock64() >> 11) % kColWarps) == warp)
-                    {
-                        ctl_store(s_ctl + 1, ld_relaxed_gpu(ctr + CTR_Q_TAIL));
-                        ctl_store(s_ctl + 2, ld_relaxed_gpu(ctr + CTR_CAND_TAIL));
-                        if (ld_relaxed_gpu(ctr + CTR_Q_STOP)) ctl_store(s_ctl, 1u);
-                    }
+                    //     slice. The CTA's control warp keeps a copy in shared memory fresh (aux_loop); everybody
+                    //     else reads that.
                     if (ctl_load(s_ctl))
                     {
                         state = 1;
-                        break;
-                    }
-                    // (3) Still nothing after a while: candidates of this warp's blocks may be waiting for their triangle
-                    //     tests (narrow_owned_blocks) -- leave the poll loop for them (state 2)
-                    if ((spins & 15u) == 0 &&
-                        ((uint64_t)gw + (uint64_t)cnext * total_warps + 1) * kCandBlock <= ctl_load(s_ctl + 2))
-                    {
-                        state = 2;
                         break;
                     }
                     if (spins > (1u << 22))
@@ -850,29 +910,13 @@ __device__ void traverse_queue(Emit& e, const uint32_t* s_lv, uint32_t* s_hist, 
                     e.retire = 0;
                 }
                 uint32_t spins = 0;
-                while (!ctl_load(s_ctl) && ++spins < (1u << 22))
-                {
-                    if ((((uint32_t)clock64() >> 11) % kColWarps) == warp && ld_relaxed_gpu(ctr + CTR_Q_STOP))
-                        ctl_store(s_ctl, 1u);
-                    __nanosleep(500);
-                }
+                while (!ctl_load(s_ctl) && ++spins < (1u << 22)) __nanosleep(500);
                 state = 1;
             }
         }
         state = __shfl_sync(0xffffffffu, state, 0);
         COL_T(t1);
         COL_ADD(1, t1 - t0);
-        if (state == 2)
-        {
-            // idle: test the candidates of this warp's ready blocks, then go back to waiting for the slot
-            uint32_t ct = 0;
-            if (lane == 0) ct = ctl_load(s_ctl + 2);
-            ct = __shfl_sync(0xffffffffu, ct, 0);
-            narrow_owned_blocks(e.sh, gw, total_warps, cnext, ct, false, lane);
-            COL_T(t1n);
-            COL_ADD(4, t1n - t1);
-            continue;
-        }
         if (state) break;
         // ---- take the filled prefix of a window of this warp's next slots: one while the queue is short, up to 32
         // once there are several nodes per warp (records of different producers may become visible out of order:
@@ -1100,6 +1144,7 @@ __global__ void __launch_bounds__(kColThreads, 1)
     ObjDesc* const s_objs = s_emit.s_objs;
     __shared__ uint32_t s_lv[kObjCache * 64]; // per cached object: off[32], cnt[32]
     __shared__ uint32_t s_hist[32];           // items per tree level (statistics)
+    __shared__ uint32_t s_backlog[kNarrowWarps]; // groups of the candidate list each narrow warp has tested (aux_loop)
     __shared__ uint32_t s_ctl[3];             // CTA copy of (stop flag, queue tail, candidate tail), refreshed by one warp at a time
     for (uint32_t i = threadIdx.x; i < min(n_obj, (uint32_t)kObjCache) * 32; i += blockDim.x)
     {
@@ -1204,19 +1249,20 @@ __global__ void __launch_bounds__(kColThreads, 1)
     // CTA's seeding token keeps the traversal from being declared over while anybody is still seeding.
     __syncthreads();
     stamp();
-    traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj,
-                                 world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
+    if (warp < (uint32_t)kTravWarps)
+        traverse_queue<RECORD, SELF>(e, s_lv, s_hist, s_ctl, levels0, levels, rank, world, n_obj,
+                                     world > 1 && n_pairs <= 4096 /* many-body scenes shard the seeding instead */);
+    else
+        aux_loop(s_emit, s_ctl, s_backlog, warp, lane_id());
     __syncthreads();
     stamp();
 
     // ---- narrow phase, the rest: the traversal is over (everything pushed has been retired, and a warp retires a batch
-    // only after its candidates have their places in the list), so the tail is final; every warp tests what is left of
-    // its blocks, including a partial last one ----
+    // only after its candidates have their places in the list), so the tail is final; every warp claims what is left ----
     {
         const uint32_t lane = lane_id();
         const uint32_t n_cand = ld_relaxed_gpu(counters + CTR_CAND_TAIL);
-        const uint32_t gw = blockIdx.x * kColWarps + warp;
-        while (narrow_owned_blocks(s_emit, gw, gridDim.x * kColWarps, e.cand_next, n_cand, true, lane)) {}
+        narrow_rest(s_emit, s_backlog, n_cand, warp, lane);
     }
     __syncthreads();
     stamp();
