@@ -27,7 +27,7 @@ constexpr int kColWarps = kColThreads / 32;
 // shared copy of the queue's control words fresh; the remaining kAuxWarps - 1 NARROW warps test candidates while the
 // traversal is still producing them. Seeding before and the rest of the narrow phase after are done by all warps.
 #ifndef OIBVH_COL_AUX_WARPS
-#define OIBVH_COL_AUX_WARPS 4
+#define OIBVH_COL_AUX_WARPS 3
 #endif
 constexpr int kAuxWarps = OIBVH_COL_AUX_WARPS;
 constexpr int kTravWarps = kColWarps - kAuxWarps;
@@ -484,6 +484,7 @@ __device__ __forceinline__ void aux_loop(const EmitShared& sh, volatile uint32_t
         }
         stop = __shfl_sync(0xffffffffu, stop, 0);
         tail = min(__shfl_sync(0xffffffffu, tail, 0), sh.cand_cap);
+        if (stop) break; // the traversal is over: what is left is shared out among all the warps (narrow_rest)
         const uint64_t g = (uint64_t)nw + (uint64_t)k * NW;
         if ((g + 1) * 32u <= tail)
         {
@@ -491,7 +492,6 @@ __device__ __forceinline__ void aux_loop(const EmitShared& sh, volatile uint32_t
             k++;
             continue;
         }
-        if (stop) break;
         __nanosleep(400);
     }
     if (lane == 0) s_backlog[a] = k; // where the CTA's warps take over (narrow_rest)

@@ -16,7 +16,7 @@ ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
 ob._lib.oibvh_debug_collide_hops(hops.ctypes.data_as(ctypes.c_void_p), 1)
 sc.detect_async(4, 0); print("counts", sc.counts(), "phase cycles", sc.phase_cycles())
 ob._lib.oibvh_debug_collide_profile(buf.ctypes.data_as(ctypes.c_void_p), 0)
-W = 148 * 20  # traversal warps of the grid: 24 warps per CTA, 4 of them auxiliary
+W = 148 * 21  # traversal warps of the grid: 24 warps per CTA, 3 of them auxiliary
 names = ["window", "empty polls", "setup+tests", "push", "narrow", "total", "full polls", "setup alone"]
 for i, n in enumerate(names):
     print(f"  {n:12s} {int(buf[i]) / W:10.0f} cycles per warp")
