@@ -190,7 +190,8 @@ int oibvh_scene_set_shard(oibvh_scene* scene, uint32_t rank, uint32_t world);
  * (src/cuda/scene.cu:236). A coherent scene records, during one detection, a complete cut of the BVTT `cut_depth`
  * levels above the leaves (0 = default 6) and starts the following detections from it, as long as the trees are only
  * refitted / transformed (any build, added tree or changed shard records a new cut). The pair set is exactly that of
- * a detection from the roots, for any motion; the cut buffer is sized by `candidate_records` of oibvh_scene_reserve.
+ * a detection from the roots, for any motion; the cut buffer is sized by `candidate_records` of oibvh_scene_reserve
+ * (like the candidate list).
  * Scenes of more than 4096 object pairs ignore the setting. */
 int oibvh_scene_set_self_collision(oibvh_scene* scene, int enable);
 int oibvh_scene_set_coherence(oibvh_scene* scene, int enable, uint32_t cut_depth);
@@ -240,8 +241,9 @@ int oibvh_scene_get_counts(oibvh_scene* scene, uint32_t* n_pairs, uint32_t* n_ca
 int oibvh_scene_get_pairs(oibvh_scene* scene, oibvh_int_tri_pair* host_pairs);
 /* device view of the pair list of the last detection (for a collective gather by the caller) */
 int oibvh_scene_device_pairs(oibvh_scene* scene, const oibvh_int_tri_pair** dev_pairs, uint32_t* n_pairs);
-/* SM-clock cycles CTA 0 of the detection kernel spent in each phase of the last detection: [0] seeding + the one grid
- * barrier, [1] queue-driven traversal with the narrow phase fused in, [2] leaving the queue empty.
+/* SM-clock cycles CTA 0 of the detection kernel spent in each phase of the last detection: [0] seeding, [1] the
+ * queue-driven traversal (with the narrow warps testing candidates beside it), [2] the rest of the narrow phase,
+ * [3] leaving the queue empty.
  * Returns the number of phases written. Replaces the reference's per-launch stopwatch (scene.cu:299-302, 419). */
 int oibvh_scene_get_phase_cycles(oibvh_scene* scene, uint32_t* cycles, uint32_t max_phases, uint32_t* n_phases);
 /* device view of the counter block of the last detection: word 0 = candidates, word 1 = pairs (lets a caller chain

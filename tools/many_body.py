@@ -64,7 +64,7 @@ def main():
     npairs, ncand = sc.counts()
     print(f"transform_many {us_x:.1f} us, refit_many {us_r:.1f} us, detect {us_d:.1f} us "
           f"(candidates {ncand}, pairs {npairs}, rounds {sc.round_stats()})")
-    print("  detect phase cycles (seeds, rounds..., narrow):", sc.phase_cycles())
+    print("  detect phase cycles (seeds, traversal, narrow rest, clean-up):", sc.phase_cycles())
     def frame():
         ob.transform_many(trees, mats); ob.refit_many(trees); sc.detect_async(4, 0)
     print(f"frame (transform + refit + detect): {timed(ctx, stream, frame):.1f} us")
