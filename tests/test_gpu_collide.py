@@ -140,6 +140,24 @@ def test_queue_growth_on_overflow(ctx, port):
     assert np.array_equal(sc.canonical_pairs(), want)
 
 
+def test_every_queue_regrows_from_the_smallest_reservation(ctx, port):
+    """work queue, candidate list and pair list all start at the minimum (2^16 records) on a contact that needs several
+    times that in each: the detection is repeated with larger buffers until nothing overflows, and loses nothing"""
+    pos, faces = meshgen.blob(120, 80, seed=4)
+    meshes = [(pos, faces), (pos.copy(), faces.copy())]  # coincident: every triangle touches its neighbours' copies
+    want, ncand = oracle_pairs(port, meshes)
+    assert ncand > 3 * (1 << 16) and len(want) > (1 << 16)
+    sc, _ = make_scene(ctx, meshes)
+    sc.reserve(1 << 16, 1 << 16, 1 << 16)
+    sc.detectCollision(ob.DeviceType.GPU0, 4, 0)
+    assert sc.getCandidateCount() == ncand
+    assert np.array_equal(sc.canonical_pairs(), want)
+    # the grown buffers are kept: the next detection needs no repeat and gives the same set
+    sc.detect_async(4, 0)
+    assert sc.counts() == (len(want), ncand)
+    assert np.array_equal(sc.canonical_pairs(), want)
+
+
 def test_shards_partition_the_pair_set(ctx, port):
     pos, faces = meshgen.blob(80, 64, seed=10)
     posB = port.transform_positions(pos, ob.mat_translate(ob.mat_identity(), (0.7, 0.2, 0.1)))
