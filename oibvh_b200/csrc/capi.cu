@@ -21,6 +21,15 @@ using namespace oibvh;
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
+// which sort a tree gets: the cooperative single-wave LSD sort (sort_lsd.cu) when all its keys fit one wave of the
+// machine, the streaming onesweep passes (tree_kernels.cu) above. OIBVH_STREAMING_SORT=1 forces the streaming sort for
+// every size (measurement only: DESIGN.md section 3.3 quotes both at T = 2^20).
+static bool single_wave_sort(uint32_t T)
+{
+    static const bool force_streaming = getenv("OIBVH_STREAMING_SORT") != nullptr;
+    return !force_streaming && T <= lsd_sort_capacity();
+}
+
 static int fail(int code, const char* fmt, ...)
 {
     char buf[512];
@@ -293,7 +302,7 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
     const uint32_t tiles = onesweep_tiles(T);
     const size_t radix = (size_t)1 << kRadixBits;
     // control block of the streaming sort (trees beyond the single-wave capacity): digit histograms, tickets, tile status
-    t->sort_ctl_words = T <= lsd_sort_capacity() ? 64 : kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix;
+    t->sort_ctl_words = single_wave_sort(T) ? 64 : kRadixPasses * radix + 64 + (size_t)kRadixPasses * tiles * radix;
     t->small = T <= kSmallTreeMax;
     int rc = OIBVH_OK;
     // round the index buffers up to whole 16-byte groups so that 128-bit accesses of the last group stay in bounds
@@ -303,7 +312,7 @@ int tree_alloc(oibvh_ctx* ctx, uint32_t V, uint32_t T, const float mesh_aabb[6],
         (rc = dev_alloc(&t->faces, T4 * 3)) || (rc = dev_alloc(&t->nodes, (size_t)t->N * 6)) ||
         (rc = dev_alloc(&t->keys_a, T4)) || (rc = dev_alloc(&t->vals_a, T4)) ||
         (t->small ? (rc = dev_alloc(&t->d_small, 1))
-                  : ((T <= lsd_sort_capacity()
+                  : ((single_wave_sort(T)
                           ? (rc = dev_alloc(&t->sort_rec, 2 * T4))                                       // single-wave sort
                           : ((rc = dev_alloc(&t->keys_b, T4)) || (rc = dev_alloc(&t->vals_b, T4)))) ||   // streaming sort
                      (rc = dev_alloc(&t->sort_ctl, t->sort_ctl_words)) ||
