@@ -397,6 +397,27 @@ def reference_gpu_baseline(pos, faces, frames=12, keep=None):
 
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
+def bind_to_gpu_cpus(dev):
+    """N > 1: run this rank on the CPUs next to its GPU (NVML's CPU affinity of the device), BEFORE any pinned buffer is
+    allocated, so that the end-to-end uploads are served by the memory of the GPU's own socket. Without it every rank's
+    pinned buffers land wherever torchrun happened to start the process, and at N = 8 half of the uploads cross the
+    socket interconnect. Best effort: returns a short description, or None when NVML / affinity are not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs ({min(cpus)}-{max(cpus)})"
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------------------
 class Gpu:
     """device, context, stream and the rank plumbing shared by every scenario"""
@@ -422,6 +443,7 @@ class Gpu:
         assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world} (launch with torchrun for N>1)"
         self.dev = local_rank if self.world > 1 else 0
         torch.cuda.set_device(self.dev)
+        self.numa = bind_to_gpu_cpus(self.dev) if self.world > 1 else None
         self.ctx = ob.Context(self.dev)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
 
@@ -877,6 +899,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "e2e_double_buffered": {"value": e2e_pipe_ms, "unit": UNIT,
                                     "note": "next step's H2D enqueued under this step's kernels; same bytes per step"},
+            "cpu_binding": g.numa,
             "roofline": {"bound": "hbm", "kernel": dominant + " -- the kernel with the largest share of the frame",
                          "achieved": dk["achieved"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
                          "traffic": dk["traffic"], "traffic_source": "committed ncu --set full capture "
