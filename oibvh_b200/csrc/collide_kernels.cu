@@ -7,8 +7,9 @@
 //                                                                    (== third/gProximity/cuda_intersect_tritri.h:350-434)
 // Design: BVTT nodes are 16-byte (objA, objB, nodeA, nodeB) records with tree nodes addressed as (level, position), so no
 // implicit<->real conversion is needed. The front is ONE work queue in device memory that the persistent warps of a
-// single cooperative launch fill and drain without grid barriers (see traverse_queue); the narrow phase runs inside the
-// same warps on the leaf pairs they find. Nothing visits the host between the seeds and the pair list.
+// single cooperative launch fill and drain without grid barriers (see traverse_queue); leaf pairs whose boxes overlap go
+// to a candidate list that dedicated warps of the same launch test while the traversal is still running (aux_loop).
+// Nothing visits the host between the seeds and the pair list.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,8 +17,8 @@ namespace oibvh
 {
 
 // One persistent cooperative kernel runs the whole detection: seeds -> queue-driven traversal with the narrow phase
-// fused in; no grid barrier anywhere (cooperative launch only guarantees that every CTA is resident, which the
-// queue's polling consumers rely on). One CTA of 512 threads per SM: the kernel needs 128 registers per thread.
+// beside it; no grid barrier anywhere (cooperative launch only guarantees that every CTA is resident, which the
+// queue's polling consumers rely on). One CTA of 768 threads per SM at 80 registers per thread.
 #ifndef OIBVH_COL_THREADS
 #define OIBVH_COL_THREADS 768
 #endif

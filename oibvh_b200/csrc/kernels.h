@@ -162,7 +162,7 @@ cudaError_t launch_mgpu_open(uint32_t* counters, uint32_t* state, cudaStream_t s
 
 // Whole detection in one cooperative launch: seeds (one root pair per object pair i<j, or every node pair of level
 // levels0 when levels0 > kMaxExpandLevels) -> queue-driven traversal (root pairs descend levels0 levels, the others
-// `levels`; rank/world shard the children of the root pairs) with the narrow phase fused in. `queue` must hold the
+// `levels`; rank/world shard the children of the root pairs) with the narrow phase beside it (opt.cand = candidate list). `queue` must hold the
 // empty marker (all bits set) in every slot -- the kernel leaves it so --, counters must be zeroed before the launch.
 // grid_blocks comes from collide_configure().
 cudaError_t collide_configure(int* grid_blocks);
